@@ -1,0 +1,139 @@
+/* SPDX-License-Identifier: Apache-2.0
+ *
+ * xntt - C ABI of the B200-native 64-bit NTT that drops in behind the sve-ntt ("sventt") API.
+ *
+ * The reference (Terminus-IMRC/sve-ntt) is a header-only C++20 template library with no FFI of its
+ * own; its boundary for this path is sventt::NTT<kernel_type> (include/sventt/wrapper.hpp:13-83).
+ * Each entry point below names the reference interface it stands in for.  The C++ front-end in
+ * sve-ntt_b200/host/sventt/ re-creates the reference's template surface on top of these calls.
+ *
+ * Conventions
+ *   - residues are uint64_t in [0, p); forward = natural order in, bit-reversed order out;
+ *     inverse = bit-reversed in, natural out, multiplied by inverse_factor^-1 (pass 1 for the
+ *     reference's "unscaled" inverse, m for the scaled one) - word for word the function computed by
+ *     NTTReference (tests/ntt-reference.hpp:43-83).
+ *   - "device" entry points take device pointers and a cudaStream_t passed as void*; they are
+ *     asynchronous with respect to the host.  "host" entry points take ordinary host pointers and
+ *     include both PCIe copies; they return after the result is in dst.
+ *   - a plan owns its twiddle tables and scratch; one plan may be used from one stream at a time.
+ *   - every function returns XNTT_OK (0) or a negative xntt_status; nothing throws across the ABI.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     XNTT_ERR_CUDA.
+ */
+#ifndef XNTT_H_INCLUDED
+#define XNTT_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum xntt_status {
+  XNTT_OK = 0,
+  XNTT_ERR_INVALID = -1,     /* bad argument / shape (reference: std::invalid_argument)            */
+  XNTT_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented here                       */
+  XNTT_ERR_ALLOC = -3,       /* device or host allocation failed (reference: std::bad_alloc)       */
+  XNTT_ERR_CUDA = -4,        /* CUDA runtime error, see xntt_last_cuda_error()                     */
+  XNTT_ERR_STATE = -5        /* direction not enabled in this plan (reference: std::logic_error)   */
+} xntt_status;
+
+enum { XNTT_ENABLE_FORWARD = 1, XNTT_ENABLE_INVERSE = 2 };
+
+#define XNTT_MAX_SPLITS 4
+
+/* Transform descriptor: what the reference spells as template arguments
+ * (Modulus<p, g>, the transform length m, the layer decomposition, inverse_factor) plus the CUDA
+ * device.  Zero-initialise, then fill in. */
+typedef struct xntt_desc {
+  uint64_t modulus;        /* p, prime; Modulus<p, g> (include/sventt/modulus.hpp:14)               */
+  uint64_t generator;      /* g, primitive root of p                                                */
+  uint32_t log2_m;         /* transform length m = 2^log2_m, 1 <= log2_m <= 31                      */
+  uint32_t batch;          /* number of back-to-back transforms in one buffer (0 means 1)           */
+  uint64_t inverse_factor; /* inverse output is divided by this (0 or 1: unscaled); the reference's */
+                           /* inverse_factor layer argument (layer/sve/radix-eight.hpp:19)          */
+  uint32_t flags;          /* XNTT_ENABLE_*; 0 means both (wrapper.hpp:34-35)                        */
+  int32_t device;          /* CUDA device ordinal, -1 = current                                     */
+  uint32_t n_splits;       /* 0 = let the planner decompose m; else the six-step decomposition      */
+  uint32_t split_log2[XNTT_MAX_SPLITS]; /* m = prod 2^split_log2[i], outermost (column) first       */
+  /* sharded plans (one process per GPU): this rank holds columns                                   */
+  /* [shard_rank * n1 / shard_count, ...) of the first split's n0 x n1 matrix. 0/0 = not sharded.   */
+  uint32_t shard_count;
+  uint32_t shard_rank;
+} xntt_desc;
+
+typedef struct xntt_plan xntt_plan;
+
+/* sventt::NTT<kernel>::NTT(enable_forward, enable_inverse, huge_pages)  (wrapper.hpp:34-46):
+ * builds every twiddle table on the device. */
+int xntt_plan_create(xntt_plan** plan, const xntt_desc* desc);
+int xntt_plan_destroy(xntt_plan* plan);
+
+/* sventt::NTT<kernel>::get_m()  (wrapper.hpp:48) */
+uint64_t xntt_plan_m(const xntt_plan* plan);
+uint32_t xntt_plan_batch(const xntt_plan* plan);
+/* number of kernel launches one forward / inverse call makes (for bench accounting) */
+uint32_t xntt_plan_launches(const xntt_plan* plan, int inverse);
+/* fills out[0..n) with the log2 sizes of the passes, returns the pass count */
+uint32_t xntt_plan_splits(const xntt_plan* plan, uint32_t* out, uint32_t n);
+
+/* sventt::NTT<kernel>::compute_forward(dst, src) / compute_forward(dst)  (wrapper.hpp:50-65).
+ * dst == src is the in-place form.  Device pointers, 16-byte aligned, m * batch words. */
+int xntt_forward(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
+/* sventt::NTT<kernel>::compute_inverse(dst, src) / compute_inverse(dst)  (wrapper.hpp:67-82) */
+int xntt_inverse(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
+
+/* The same two calls on host buffers: H2D copy, transform, D2H copy, synchronise. */
+int xntt_forward_host(const xntt_plan* plan, uint64_t* dst, const uint64_t* src);
+int xntt_inverse_host(const xntt_plan* plan, uint64_t* dst, const uint64_t* src);
+
+/* Sharded plans only: the two local halves of a forward (A: column passes on the local column
+ * block, then the caller's all-to-all, then B: row transforms on the local row block) and of an
+ * inverse (B^-1, all-to-all, A^-1).  Layouts are described in DESIGN.md. */
+int xntt_shard_forward_cols(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
+int xntt_shard_forward_rows(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
+int xntt_shard_inverse_rows(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
+int xntt_shard_inverse_cols(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
+
+/* PAdic64 element-wise helpers on device buffers (count words each):
+ *   to_montgomery      : dst[i] = src[i] * 2^64 mod p     (modmul/sve/p-adic-64.hpp:19-22)
+ *   from_montgomery    : dst[i] = src[i] * 2^-64 mod p    (p-adic-64.hpp:24-38, canonical result)
+ *   multiply_normalize : dst[i] = a[i] * b_mont[i] * 2^-64 mod p, canonical  (p-adic-64.hpp:101-115);
+ *                        with b_mont = to_montgomery(b) this is the point-wise product a[i]*b[i]
+ *                        used between the transforms of a polynomial multiply
+ *                        (examples/magic-series/gaussian-polynomial.hpp:201-212). */
+int xntt_to_montgomery(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, size_t count, void* stream);
+int xntt_from_montgomery(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, size_t count, void* stream);
+int xntt_multiply_normalize(const xntt_plan* plan, uint64_t* dst, const uint64_t* a, const uint64_t* b_mont,
+                            size_t count, void* stream);
+
+/* Device-resident PageMemory twin (include/sventt/vector.hpp:61-168): pinned host memory for the
+ * host entry points / device memory for the device ones. */
+int xntt_alloc_device(void** ptr, size_t bytes, int device);
+int xntt_free_device(void* ptr);
+int xntt_alloc_pinned(void** ptr, size_t bytes);
+int xntt_free_pinned(void* ptr);
+int xntt_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream);
+int xntt_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes, void* stream);
+int xntt_stream_synchronize(void* stream);
+
+const char* xntt_strerror(int status);
+/* last cudaError_t seen by this thread inside the library, as text */
+const char* xntt_last_cuda_error(void);
+/* "xntt <version> sm_100a" */
+const char* xntt_version(void);
+/* number of CUDA devices visible, or a negative xntt_status */
+int xntt_device_count(void);
+
+/* Micro-benchmarks that calibrate the integer roofline (tools/ and bench.py): run `iters`
+ * dependent-free rounds of the named instruction mix in registers on every SM and return the
+ * achieved rate in giga-operations per second in *gops.  kind: 0 = IMAD (32-bit mad.lo),
+ * 1 = IMAD.WIDE, 2 = IADD3, 3 = Montgomery butterflies (gops = butterflies/s / 1e9). */
+int xntt_microbench(int kind, int iters, double* gops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* XNTT_H_INCLUDED */

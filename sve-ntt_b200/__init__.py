@@ -1,0 +1,210 @@
+# SPDX-License-Identifier: Apache-2.0
+"""ctypes binding of libxntt.so (include/xntt.h) - plumbing for tests/ and bench.py.
+
+The product is the C-ABI library plus the C++20 front-end in ``host/sventt``; this module only
+hands raw device pointers (e.g. ``torch.Tensor.data_ptr()``) and stream handles to it.  There is no
+CPU path here: if the CUDA library has not been built, importing succeeds but ``load()`` raises.
+
+The directory name carries a hyphen, so load it with ``__graft_entry__.load_package()``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libxntt.so")
+
+P0 = 0xFFFFFC6E80000001  # 2^64 - 1827*2^31 + 1 (reference README.md:19)
+G0 = 3
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_ALLOC, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5
+ENABLE_FORWARD, ENABLE_INVERSE = 1, 2
+MAX_SPLITS = 4
+
+
+class XnttError(RuntimeError):
+    def __init__(self, status, what, detail=""):
+        self.status = status
+        super().__init__(f"{what}: status {status}" + (f" ({detail})" if detail else ""))
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("modulus", C.c_uint64),
+        ("generator", C.c_uint64),
+        ("log2_m", C.c_uint32),
+        ("batch", C.c_uint32),
+        ("inverse_factor", C.c_uint64),
+        ("flags", C.c_uint32),
+        ("device", C.c_int32),
+        ("n_splits", C.c_uint32),
+        ("split_log2", C.c_uint32 * MAX_SPLITS),
+        ("shard_count", C.c_uint32),
+        ("shard_rank", C.c_uint32),
+    ]
+
+
+# every symbol include/xntt.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_U64P = C.c_void_p  # raw addresses (device or host)
+SYMBOLS = {
+    "xntt_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(Desc)]),
+    "xntt_plan_destroy": (C.c_int, [_P]),
+    "xntt_plan_m": (C.c_uint64, [_P]),
+    "xntt_plan_batch": (C.c_uint32, [_P]),
+    "xntt_plan_launches": (C.c_uint32, [_P, C.c_int]),
+    "xntt_plan_splits": (C.c_uint32, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
+    "xntt_forward": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_inverse": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_forward_host": (C.c_int, [_P, _U64P, _U64P]),
+    "xntt_inverse_host": (C.c_int, [_P, _U64P, _U64P]),
+    "xntt_shard_forward_cols": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_shard_forward_rows": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_shard_inverse_rows": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_shard_inverse_cols": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_to_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
+    "xntt_from_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
+    "xntt_multiply_normalize": (C.c_int, [_P, _U64P, _U64P, _U64P, C.c_size_t, _P]),
+    "xntt_alloc_device": (C.c_int, [C.POINTER(_P), C.c_size_t, C.c_int]),
+    "xntt_free_device": (C.c_int, [_P]),
+    "xntt_alloc_pinned": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "xntt_free_pinned": (C.c_int, [_P]),
+    "xntt_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "xntt_memcpy_d2h": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "xntt_stream_synchronize": (C.c_int, [_P]),
+    "xntt_strerror": (C.c_char_p, [C.c_int]),
+    "xntt_last_cuda_error": (C.c_char_p, []),
+    "xntt_version": (C.c_char_p, []),
+    "xntt_device_count": (C.c_int, []),
+    "xntt_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+
+class Library:
+    """A loaded libxntt (or, in the CPU test-suite only, the host emulator built from the same
+    sources)."""
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        self.path = path
+        self.lib = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(self.lib, name)  # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+
+    def check(self, status, what):
+        if status != OK:
+            detail = self.lib.xntt_strerror(status).decode()
+            if status == ERR_CUDA or status == ERR_ALLOC:
+                detail += ": " + self.lib.xntt_last_cuda_error().decode()
+            raise XnttError(status, what, detail)
+
+    def version(self):
+        return self.lib.xntt_version().decode()
+
+    def device_count(self):
+        return self.lib.xntt_device_count()
+
+    def plan(self, log2_m, **kw):
+        return Plan(self, log2_m, **kw)
+
+    def microbench(self, kind, iters):
+        g, ms = C.c_double(), C.c_double()
+        self.check(self.lib.xntt_microbench(kind, iters, C.byref(g), C.byref(ms)), "xntt_microbench")
+        return g.value, ms.value
+
+
+class Plan:
+    """sventt::NTT<kernel> (include/sventt/wrapper.hpp:13-83) over raw pointers."""
+
+    def __init__(self, library, log2_m, modulus=P0, generator=G0, batch=1, inverse_factor=None,
+                 forward=True, inverse=True, device=-1, splits=None, shard_count=0, shard_rank=0):
+        self.L = library
+        d = Desc()
+        d.modulus, d.generator = modulus, generator
+        d.log2_m, d.batch = log2_m, batch
+        d.inverse_factor = (1 << log2_m) if inverse_factor is None else inverse_factor
+        d.flags = (ENABLE_FORWARD if forward else 0) | (ENABLE_INVERSE if inverse else 0)
+        d.device = device
+        if splits:
+            d.n_splits = len(splits)
+            for i, s in enumerate(splits):
+                d.split_log2[i] = s
+        d.shard_count, d.shard_rank = shard_count, shard_rank
+        self.desc = d
+        self.h = C.c_void_p()
+        library.check(library.lib.xntt_plan_create(C.byref(self.h), C.byref(d)), "xntt_plan_create")
+        self.m = library.lib.xntt_plan_m(self.h)
+        self.batch = library.lib.xntt_plan_batch(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.lib.xntt_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def splits(self):
+        buf = (C.c_uint32 * MAX_SPLITS)()
+        n = self.L.lib.xntt_plan_splits(self.h, buf, MAX_SPLITS)
+        return [int(buf[i]) for i in range(n)]
+
+    @property
+    def launches(self):
+        return int(self.L.lib.xntt_plan_launches(self.h, 0))
+
+    def _call(self, name, *args):
+        self.L.check(getattr(self.L.lib, name)(self.h, *args), name)
+
+    # device pointers (ints) + stream handle (int)
+    def forward(self, dst, src, stream=0):
+        self._call("xntt_forward", dst, src, stream)
+
+    def inverse(self, dst, src, stream=0):
+        self._call("xntt_inverse", dst, src, stream)
+
+    def forward_host(self, dst, src):
+        self._call("xntt_forward_host", dst, src)
+
+    def inverse_host(self, dst, src):
+        self._call("xntt_inverse_host", dst, src)
+
+    def shard_forward_cols(self, dst, src, stream=0):
+        self._call("xntt_shard_forward_cols", dst, src, stream)
+
+    def shard_forward_rows(self, dst, src, stream=0):
+        self._call("xntt_shard_forward_rows", dst, src, stream)
+
+    def shard_inverse_rows(self, dst, src, stream=0):
+        self._call("xntt_shard_inverse_rows", dst, src, stream)
+
+    def shard_inverse_cols(self, dst, src, stream=0):
+        self._call("xntt_shard_inverse_cols", dst, src, stream)
+
+    def to_montgomery(self, dst, src, count, stream=0):
+        self._call("xntt_to_montgomery", dst, src, count, stream)
+
+    def from_montgomery(self, dst, src, count, stream=0):
+        self._call("xntt_from_montgomery", dst, src, count, stream)
+
+    def multiply_normalize(self, dst, a, b_mont, count, stream=0):
+        self._call("xntt_multiply_normalize", dst, a, b_mont, count, stream)
+
+
+_default = None
+
+
+def load():
+    """The CUDA library; raises if it has not been built (no fallback)."""
+    global _default
+    if _default is None:
+        _default = Library(LIB_PATH)
+    return _default

@@ -1,0 +1,33 @@
+// SPDX-License-Identifier: Apache-2.0
+// The device back-end as the planner sees it: memory, streams and kernel launches, with no CUDA
+// types in the signatures.  backend_cuda.cu is the product implementation (sm_100a kernels);
+// tests/emu/backend_emu.cpp executes the very same kernel templates on the host, one emulated
+// thread at a time, so that the planner and the index algebra are covered by the CPU test-suite.
+#pragma once
+#include "params.h"
+
+namespace xntt {
+namespace be {
+
+// every function returns 0 on success; on failure last_error() describes it
+int device_count(int* n);
+int get_device(int* dev);
+int set_device(int dev);
+int dev_malloc(void** p, size_t bytes);   // returns 2 for out-of-memory, 1 for other errors
+int dev_free(void* p);
+int host_malloc_pinned(void** p, size_t bytes);
+int host_free_pinned(void* p);
+int memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int stream_sync(void* stream);
+const char* last_error();
+
+int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void* stream);
+int launch_gen_table(Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t, void* stream);
+int launch_to_mont(u64* dst, const u64* src, size_t n, u64 r2, void* stream);
+int launch_from_mont(u64* dst, const u64* src, size_t n, void* stream);
+int launch_mulnorm(u64* dst, const u64* a, const u64* b, size_t n, void* stream);
+int microbench(int kind, int iters, double* gops, double* ms);
+
+}  // namespace be
+}  // namespace xntt

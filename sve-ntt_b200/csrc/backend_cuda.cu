@@ -1,0 +1,265 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// CUDA implementation of backend.h: memory, streams, the small kernels (twiddle generation,
+// element-wise PAdic64 helpers, register micro-benchmarks) and the pass-kernel dispatcher.
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "backend.h"
+#include "dispatch.cuh"
+#include "misc_kernels.cuh"
+
+namespace xntt {
+
+static thread_local std::string g_err = "no error";
+static int fail(cudaError_t e) {
+  g_err = cudaGetErrorString(e);
+  return e == cudaErrorMemoryAllocation ? 2 : 1;
+}
+#define CU(call)                              \
+  do {                                        \
+    cudaError_t e_ = (call);                  \
+    if (e_ != cudaSuccess) return fail(e_);   \
+  } while (0)
+
+template <class F>
+__global__ void gen_table_kernel(Tw* out, u32 count, int kind, int logn, int shift, const __grid_constant__ PowTable t) {
+  const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < count) out[idx] = table_entry<F>(idx, kind, logn, shift, t);
+}
+template <class F>
+__global__ void to_mont_kernel(u64* dst, const u64* src, size_t n, u64 r2) {
+  const u64 r2p = F::companion(r2);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = ew_to_mont<F>(src[i], r2, r2p);
+}
+template <class F>
+__global__ void from_mont_kernel(u64* dst, const u64* src, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = ew_from_mont<F>(src[i]);
+}
+template <class F>
+__global__ void mulnorm_kernel(u64* dst, const u64* a, const u64* b, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = ew_mulnorm<F>(a[i], b[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Register-resident micro-benchmarks (calibrate the integer roofline on the box).
+template <int KIND>
+__global__ void __launch_bounds__(256) microbench_kernel(u64* out, int iters, u32 a, u32 b) {
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if constexpr (KIND == 0) {
+    u32 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = tid + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = x[i] * a + b;
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= x[i];
+    if (s == 0x12345u) out[tid] = s;
+  } else if constexpr (KIND == 1) {
+    u64 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = ((u64)tid << 32) + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (u64)(u32)x[i] * a + x[i];
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= x[i];
+    if (s == 0x12345u) out[tid] = s;
+  } else if constexpr (KIND == 2) {
+    u32 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = tid + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(x[i]) : "r"(a), "r"(b));
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= x[i];
+    if (s == 0x12345u) out[tid] = s;
+  } else if constexpr (KIND == 3) {
+    u64 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = ((u64)tid << 32) + i * 0x9e3779b97f4a7c15ull;
+    const u64 w = (((u64)a << 32) | b) % F0::P, wp = F0::companion(w);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) F0::ct_butterfly(x[i], x[i + 1], w, wp);
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= x[i];
+    if (s == 0x12345u) out[tid] = s;
+  } else {
+    // IMAD and LOP3 interleaved 1:1 (dual-pipe issue test)
+    u32 x[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = tid + i, y[i] = tid * 3 + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          x[i] = x[i] * a + b;
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(y[i]) : "r"(a), "r"(b));
+        }
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= x[i] ^ y[i];
+    if (s == 0x12345u) out[tid] = s;
+  }
+}
+
+
+namespace be {
+
+int device_count(int* n) {
+  CU(cudaGetDeviceCount(n));
+  return 0;
+}
+int get_device(int* dev) {
+  CU(cudaGetDevice(dev));
+  return 0;
+}
+int set_device(int dev) {
+  CU(cudaSetDevice(dev));
+  return 0;
+}
+int dev_malloc(void** p, size_t bytes) {
+  CU(cudaMalloc(p, bytes ? bytes : 16));
+  return 0;
+}
+int dev_free(void* p) {
+  if (p) CU(cudaFree(p));
+  return 0;
+}
+int host_malloc_pinned(void** p, size_t bytes) {
+  CU(cudaMallocHost(p, bytes ? bytes : 16));
+  return 0;
+}
+int host_free_pinned(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return 0;
+}
+int memcpy_h2d(void* dst, const void* src, size_t bytes, void* st) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)st));
+  return 0;
+}
+int memcpy_d2h(void* dst, const void* src, size_t bytes, void* st) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)st));
+  return 0;
+}
+int stream_sync(void* st) {
+  CU(cudaStreamSynchronize((cudaStream_t)st));
+  return 0;
+}
+const char* last_error() { return g_err.c_str(); }
+
+int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (col)
+    e = inverse ? launch_inv_col(logn, prm, grid, st) : launch_fwd_col(logn, prm, grid, st);
+  else
+    e = inverse ? launch_inv_row(logn, prm, grid, st) : launch_fwd_row(logn, prm, grid, st);
+  if (e != cudaSuccess) return fail(e);
+  return 0;
+}
+
+int launch_gen_table(Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t, void* stream) {
+  const u32 threads = 128, blocks = (count + threads - 1) / threads;
+  gen_table_kernel<F0><<<blocks, threads, 0, (cudaStream_t)stream>>>(out, count, kind, logn, shift, t);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static unsigned ew_grid(size_t n) {
+  size_t b = (n + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return b ? (unsigned)b : 1u;
+}
+int launch_to_mont(u64* dst, const u64* src, size_t n, u64 r2, void* st) {
+  to_mont_kernel<F0><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(dst, src, n, r2);
+  CU(cudaGetLastError());
+  return 0;
+}
+int launch_from_mont(u64* dst, const u64* src, size_t n, void* st) {
+  from_mont_kernel<F0><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(dst, src, n);
+  CU(cudaGetLastError());
+  return 0;
+}
+int launch_mulnorm(u64* dst, const u64* a, const u64* b, size_t n, void* st) {
+  mulnorm_kernel<F0><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(dst, a, b, n);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int microbench(int kind, int iters, double* gops, double* ms_out) {
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned blocks = (unsigned)sms * 8, threads = 256;
+  u64* out = nullptr;
+  CU(cudaMalloc(&out, (size_t)blocks * threads * sizeof(u64)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(e0, 0));
+    switch (kind) {
+      case 0:
+        microbench_kernel<0><<<blocks, threads>>>(out, iters, 0x9e3779b1u, 0x7f4a7c15u);
+        break;
+      case 1:
+        microbench_kernel<1><<<blocks, threads>>>(out, iters, 0x9e3779b1u, 0x7f4a7c15u);
+        break;
+      case 2:
+        microbench_kernel<2><<<blocks, threads>>>(out, iters, 0x9e3779b1u, 0x7f4a7c15u);
+        break;
+      case 3:
+        microbench_kernel<3><<<blocks, threads>>>(out, iters, 0x9e3779b1u, 0x7f4a7c15u);
+        break;
+      default:
+        microbench_kernel<4><<<blocks, threads>>>(out, iters, 0x9e3779b1u, 0x7f4a7c15u);
+        break;
+    }
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventSynchronize(e1));
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, e0, e1));
+    if (rep > 0 && t < best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  const double per_thread = kind == 3 ? 4.0 * iters : (kind == 4 ? 128.0 * iters : 64.0 * iters);
+  *gops = per_thread * blocks * threads / (best * 1e-3) / 1e9;
+  if (ms_out) *ms_out = best;
+  return 0;
+}
+
+
+}  // namespace be
+}  // namespace xntt

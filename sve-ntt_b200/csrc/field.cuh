@@ -1,0 +1,201 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// PAdic64 device arithmetic for sm_100a: Montgomery multiplication with R = 2^64 built from
+// 32-bit IMAD / IMAD.WIDE chains, plus the "lazy" add/sub used by the butterflies.
+//
+// Values ("residues") live in one of two domains:
+//   canonical : v in [0, P)
+//   lazy      : any v in [0, 2^64), standing for v mod P.  Because P + C = 2^64 (C = 2^64 - P),
+//               a single carry/borrow out of a 64-bit add/sub is repaired by adding/subtracting C.
+//
+// What this replaces in the reference (value-for-value, not instruction-for-instruction):
+//   sventt::PAdic64SVE::multiply            include/sventt/modmul/sve/p-adic-64.hpp:80-95
+//   sventt::PAdic64SVE::multiply_normalize  include/sventt/modmul/sve/p-adic-64.hpp:101-115
+//   sventt::PAdic64SVE::butterfly_inverse   include/sventt/modmul/sve/p-adic-64.hpp:229-246
+//   sventt::PAdic64SVE::precompute          include/sventt/modmul/sve/p-adic-64.hpp:64-74
+// Twiddles are kept, like the reference does, as a pair (w, w') with w = omega * 2^64 mod P
+// (Montgomery form) and w' = w * P^-1 mod 2^64, so that mont(a, w, w') = a * omega mod P with the
+// data staying in the normal domain.
+#pragma once
+#include <cstdint>
+
+#include "params.h"
+
+#if defined(XNTT_HOST_EMU)
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __align__(n) alignas(n)
+#endif
+
+namespace xntt {
+
+__host__ __device__ constexpr u64 montgomery_inverse(u64 p) {
+  // Newton iteration for p^-1 mod 2^64 (p odd); same value as
+  // sventt::Modulus::get_montgomery_inverse (include/sventt/modulus.hpp:36-68).
+  u64 x = p;  // correct to 3 bits
+  for (int i = 0; i < 6; ++i) x *= 2 - p * x;
+  return x;
+}
+
+#if defined(XNTT_HOST_EMU)
+// Host emulation of the PTX primitives (tests/emu only: lets the CPU test-suite execute the very
+// same kernel templates thread by thread; never part of the product path).
+inline u64 pack64(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+inline void unpack64(u64 v, u32& lo, u32& hi) {
+  lo = (u32)v;
+  hi = (u32)(v >> 32);
+}
+inline u64 mulhi64(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) >> 64); }
+// (a - b) mod 2^64 and -borrow
+inline void sub_borrow_mask(u64 a, u64 b, u64& d, u32& m) {
+  d = a - b;
+  m = a < b ? 0xffffffffu : 0u;
+}
+// (a + b) mod 2^64 and carry + addend
+inline void add_carry_plus(u64 a, u64 b, u32 addend, u64& s, u32& k) {
+  s = a + b;
+  k = addend + (s < a ? 1u : 0u);
+}
+// (a - b) mod 2^64 and -sub - borrow
+inline void sub_borrow_minus(u64 a, u64 b, u32 sub, u64& d, u32& k) {
+  d = a - b;
+  k = 0u - sub - (a < b ? 1u : 0u);
+}
+#else
+__device__ __forceinline__ u64 pack64(u32 lo, u32 hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack64(u64 v, u32& lo, u32& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 mulhi64(u64 a, u64 b) { return __umul64hi(a, b); }
+// (a - b) mod 2^64 and m = -borrow (IADD3, IADD3.X, IADD3.X)
+__device__ __forceinline__ void sub_borrow_mask(u64 a, u64 b, u64& d, u32& m) {
+  u32 al, ah, bl, bh, dl, dh;
+  unpack64(a, al, ah);
+  unpack64(b, bl, bh);
+  asm("sub.cc.u32 %0, %3, %5;\n\tsubc.cc.u32 %1, %4, %6;\n\tsubc.u32 %2, 0, 0;"
+      : "=r"(dl), "=r"(dh), "=r"(m)
+      : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+  d = pack64(dl, dh);
+}
+// (a + b) mod 2^64 and k = addend + carry
+__device__ __forceinline__ void add_carry_plus(u64 a, u64 b, u32 addend, u64& s, u32& k) {
+  u32 al, ah, bl, bh, sl, sh;
+  unpack64(a, al, ah);
+  unpack64(b, bl, bh);
+  asm("add.cc.u32 %0, %3, %5;\n\taddc.cc.u32 %1, %4, %6;\n\taddc.u32 %2, %7, 0;"
+      : "=r"(sl), "=r"(sh), "=r"(k)
+      : "r"(al), "r"(ah), "r"(bl), "r"(bh), "r"(addend));
+  s = pack64(sl, sh);
+}
+// (a - b) mod 2^64 and k = -sub - borrow
+__device__ __forceinline__ void sub_borrow_minus(u64 a, u64 b, u32 sub, u64& d, u32& k) {
+  u32 al, ah, bl, bh, dl, dh;
+  unpack64(a, al, ah);
+  unpack64(b, bl, bh);
+  asm("sub.cc.u32 %0, %3, %5;\n\tsubc.cc.u32 %1, %4, %6;\n\tsubc.u32 %2, 0, %7;"
+      : "=r"(dl), "=r"(dh), "=r"(k)
+      : "r"(al), "r"(ah), "r"(bl), "r"(bh), "r"(sub));
+  d = pack64(dl, dh);
+}
+#endif
+
+// Field with a compile-time modulus.  All the lazy-domain identities below only need P < 2^64 odd;
+// the signed IMAD.WIDE correction additionally needs C_LO < 2^31, which holds for the production
+// prime P = 0xfffffc6e80000001 (C = 0x3917fffffff).
+template <u64 P_>
+struct Field {
+  static constexpr u64 P = P_;
+  static constexpr u64 C = 0 - P_;  // 2^64 - P
+  static constexpr u32 P_LO = (u32)P_, P_HI = (u32)(P_ >> 32);
+  static constexpr u32 C_LO = (u32)C, C_HI = (u32)(C >> 32);
+  static constexpr u64 PINV = montgomery_inverse(P_);
+  static constexpr bool kSignedFix = (C_LO < 0x80000000u) && (C >> 63) == 0;
+
+  // v + delta * C (mod 2^64) for delta in {-1, 0, +1} held as a 32-bit two's complement value.
+  // Maps to one IMAD.WIDE (signed) plus one IMAD.
+  static __device__ __forceinline__ u64 fix(u64 v, u32 delta) {
+    if constexpr (kSignedFix) {
+      u64 t = v + (u64)((long long)(int)delta * (long long)(int)C_LO);
+      u32 tl, th;
+      unpack64(t, tl, th);
+      th += delta * C_HI;
+      return pack64(tl, th);
+    } else {
+      // generic: delta = +1 adds C, delta = -1 adds P (== -C mod 2^64)
+      u64 add = (delta == 1u) ? C : ((delta == 0u) ? 0ull : P);
+      return v + add;
+    }
+  }
+
+  // Montgomery product pieces: returns h1 = hi64(a*w), h2 = hi64((a*w')*P); a*omega == h1 - h2 (mod P),
+  // the true difference lying in (-P, P).  `a` may be lazy.
+  static __device__ __forceinline__ void mont_parts(u64 a, u64 w, u64 wp, u64& h1, u64& h2) {
+    u64 q = a * wp;
+    h1 = mulhi64(a, w);
+    h2 = mulhi64(q, P);
+  }
+
+  // Canonical Montgomery product (reference: multiply_normalize).
+  static __device__ __forceinline__ u64 mont(u64 a, u64 w, u64 wp) {
+    u64 h1, h2, u;
+    u32 m;
+    mont_parts(a, w, wp, h1, h2);
+    sub_borrow_mask(h1, h2, u, m);
+    return fix(u, m);  // borrow -> subtract C, i.e. add P
+  }
+  static __device__ __forceinline__ u64 mont(u64 a, Tw t) { return mont(a, t.w, t.wp); }
+
+  // w' for a Montgomery-form w that was not precomputed (reference: precompute).
+  static __device__ __forceinline__ u64 companion(u64 w) { return w * PINV; }
+
+  // lazy -> canonical
+  static __device__ __forceinline__ u64 canon(u64 v) {
+    if constexpr ((P >> 63) != 0) {
+      // v >= P  <=>  v + C carries; then v - P == v + C (mod 2^64)
+      u64 t;
+      u32 c;
+      add_carry_plus(v, C, 0u, t, c);
+      return c ? t : v;
+    } else {
+      return v % P;
+    }
+  }
+
+  // Cooley-Tukey butterfly on lazy values: (x0, x1) <- (x0 + x1*omega, x0 - x1*omega).
+  // x0, x1 lazy in, lazy out.  The Montgomery correction is folded into the add/sub repair:
+  // with u = (h1 - h2) mod 2^64 and br its borrow, x1*omega = u - br*2^64, hence
+  //   x0 + x1*omega = s + (carry(s)  - br) * 2^64,  s = (x0 + u) mod 2^64
+  //   x0 - x1*omega = d + (br - borrow(d)) * 2^64,  d = (x0 - u) mod 2^64
+  // and 2^64 == C (mod P).  Range: both true values lie in (-P, 2^64 + P), so the repaired value
+  // stays inside [0, 2^64) and the final 64-bit add cannot wrap.
+  static __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, u64 w, u64 wp) {
+    u64 h1, h2, u, s, d;
+    u32 m, d0, d1;
+    mont_parts(x1, w, wp, h1, h2);
+    sub_borrow_mask(h1, h2, u, m);      // m  = -br
+    add_carry_plus(x0, u, m, s, d0);    // d0 = carry - br
+    sub_borrow_minus(x0, u, m, d, d1);  // d1 = br - borrow
+    x0 = fix(s, d0);
+    x1 = fix(d, d1);
+  }
+  static __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, Tw t) {
+    ct_butterfly(x0, x1, t.w, t.wp);
+  }
+
+  // Butterfly with omega = 1: (x0, x1) <- (x0 + x1, x0 - x1).  x0 lazy, x1 MUST be canonical.
+  static __device__ __forceinline__ void ct_butterfly_one(u64& x0, u64& x1) {
+    u64 s, d;
+    u32 d0, d1;
+    add_carry_plus(x0, x1, 0u, s, d0);    // d0 = carry
+    sub_borrow_minus(x0, x1, 0u, d, d1);  // d1 = -borrow
+    x0 = fix(s, d0);
+    x1 = fix(d, d1);
+  }
+};
+
+}  // namespace xntt

@@ -1,0 +1,66 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// Per-element bodies of the small kernels: on-device twiddle generation (north-star item 4; replaces
+// the serial host loops of every prepare_forward / prepare_inverse, e.g.
+// include/sventt/layer/sve/radix-eight.hpp:34-93 and include/sventt/layer/sve/generic.hpp:72-110)
+// and the PAdic64 element-wise helpers.
+#pragma once
+#include "field.cuh"
+#include "params.h"
+
+namespace xntt {
+
+#if defined(XNTT_HOST_EMU)
+inline u32 brev32(u32 v) {
+  u32 r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
+  return r;
+}
+inline int clz32(u32 v) { return v ? __builtin_clz(v) : 32; }
+#else
+__device__ __forceinline__ u32 brev32(u32 v) { return __brev(v); }
+__device__ __forceinline__ int clz32(u32 v) { return __clz(v); }
+#endif
+
+template <class F>
+__device__ __forceinline__ u64 pow_mont(const PowTable& t, u32 e) {
+  u64 acc = t.scale;
+#pragma unroll 1
+  for (int i = 0; e; ++i, e >>= 1)
+    if (e & 1) acc = F::mont(acc, t.sq[i], F::companion(t.sq[i]));
+  return acc;
+}
+
+// exponent of table entry idx
+__device__ __forceinline__ u32 table_exponent(u32 idx, int kind, int logn, int shift) {
+  if (kind == kFwdG) {
+    // G[b] = omega_N^bitrev_{logn-1}(b)
+    return logn > 1 ? (brev32(idx) >> (32 - (logn - 1))) : 0u;
+  } else if (kind == kInvI) {
+    // I[l + j] = (omega_N^-1)^(j * N / 2l)
+    if (idx == 0) return 0u;
+    const int ll = 31 - clz32(idx);  // log2 l
+    return (idx - (1u << ll)) << (logn - 1 - ll);
+  }
+  return idx << shift;
+}
+
+template <class F>
+__device__ __forceinline__ Tw table_entry(u32 idx, int kind, int logn, int shift, const PowTable& t) {
+  Tw r;
+  r.w = pow_mont<F>(t, table_exponent(idx, kind, logn, shift));
+  r.wp = F::companion(r.w);
+  return r;
+}
+
+// PAdic64::to_montgomery (p-adic-64.hpp:19-22): a * 2^64 mod P, r2 = 2^128 mod P
+template <class F>
+__device__ __forceinline__ u64 ew_to_mont(u64 a, u64 r2, u64 r2p) { return F::mont(a, r2, r2p); }
+// PAdic64::from_montgomery (p-adic-64.hpp:24-38), canonical
+template <class F>
+__device__ __forceinline__ u64 ew_from_mont(u64 a) { return F::mont(a, 1ull, F::PINV); }
+// PAdic64::multiply_normalize (p-adic-64.hpp:101-115) with on-the-fly precompute
+template <class F>
+__device__ __forceinline__ u64 ew_mulnorm(u64 a, u64 b) { return F::mont(a, b, F::companion(b)); }
+
+}  // namespace xntt

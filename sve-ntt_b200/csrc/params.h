@@ -1,0 +1,55 @@
+// SPDX-License-Identifier: Apache-2.0
+// Plain-C++ types shared by the planner (plan.cpp, no CUDA headers) and the kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace xntt {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// A twiddle in the reference's PAdic64 storage format (include/sventt/modmul/sve/p-adic-64.hpp:64-95):
+struct alignas(16) Tw {
+  u64 w;   // omega * 2^64 mod P         (to_montgomery)
+  u64 wp;  // w * P^-1 mod 2^64          (precompute)
+};
+
+constexpr int kThreads = 256;
+constexpr int kTileLog = 13;    // a tile holds 2^13 residues = 64 KiB of shared memory
+constexpr int kMaxRowLog = 13;  // longest transform one CTA keeps in shared memory (row mode)
+constexpr int kMaxColLog = 12;  // longest column transform (column mode, 2 columns wide)
+constexpr int kMaxTileWLog = 5;
+
+constexpr int tile_logw(int logn) {
+  return logn >= kTileLog ? 0 : (kTileLog - logn < kMaxTileWLog ? kTileLog - logn : kMaxTileWLog);
+}
+constexpr int tile_c(int logn) { return tile_logw(logn) >= 1 ? 2 : 1; }
+
+// The production prime of the reference README (README.md:19): 2^64 - 1827*2^31 + 1.
+constexpr u64 kP0 = 0xfffffc6e80000001ULL;
+
+struct PassParams {
+  const u64* src;
+  u64* dst;
+  const Tw* tw;        // forward: G[0 .. N/2), inverse: I[1 .. N)
+  const Tw* twist_lo;  // omega_M^(+-e), e < 2^twist_shift            (null when no twist)
+  const Tw* twist_hi;  // omega_M^(+-e * 2^twist_shift) (* 1/inverse_factor on the inverse side)
+  u64 inner;           // column mode: elements between consecutive k; row mode: unused
+  u64 outer_stride;    // column mode: elements between consecutive outer blocks (= N * inner)
+  u32 tiles_per_outer; // column mode: inner / W
+  u32 twist_shift;
+  u32 twist_col0;      // column mode: global index of this buffer's first column (sharded plans)
+  u32 scale_on;        // inverse row mode: multiply outputs by `scale` (else just canonicalise)
+  u32 rows;            // row mode: number of valid rows in the buffer (tiles may be ragged)
+  Tw scale;
+};
+
+// Input of the on-device table generator: out[idx] = scale * root^e(idx), Montgomery pair.
+struct PowTable {
+  u64 sq[32];  // root^(2^i) in Montgomery form
+  u64 scale;   // Montgomery form of the extra factor (2^64 mod P for none)
+};
+enum TableKind { kFwdG = 0, kInvI = 1, kPowers = 2 };
+
+}  // namespace xntt

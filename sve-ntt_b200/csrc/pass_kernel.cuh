@@ -1,0 +1,392 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// One "pass" of the (blocked) six-step NTT: every CTA owns a tile of W independent length-N
+// sub-transforms, keeps it resident in shared memory, and runs all log2(N) butterfly levels on it
+// as radix-8 (first stage radix 4/8/16) register passes with swizzled shared-memory exchanges.
+//
+//   column mode : data is [outer][N][inner]; the tile is N rows x W contiguous columns
+//                 (element (k, c) at base + k*inner + c).  This is the column phase of
+//                 sventt::BlockedGenericSVELayer::compute_forward_without_twiddle
+//                 (include/sventt/layer/sve/blocked-generic.hpp:121-155): its tile transpose-in /
+//                 inner NTT / transpose-out becomes "strided tile load -> NTT -> strided store",
+//                 and the row twiddle of sventt::GenericSVELayer::twiddle_rows_forward
+//                 (include/sventt/layer/sve/generic.hpp:169-268) is fused into the last stage.
+//   row mode    : data is [rows][N]; the tile is W whole rows (element (k, c) at base + c*N + k).
+//                 This is the inner kernel call of sventt::RecursiveNTT::compute_forward
+//                 (include/sventt/kernel/recursive.hpp:69-74).
+//
+// Butterfly network.  Forward uses Cooley-Tukey butterflies on natural-order input producing
+// bit-reversed output: level s (half-length N/2^(s+1)) multiplies the upper half of block b by
+// G[b] = omega_N^bitrev_{log2N-1}(b) - one table of N/2 entries serves every level.  Inverse is
+// decimation-in-time on bit-reversed input: level with half-length l multiplies position j by
+// I[l + j] = omega_{2l}^-j.  Both are "multiply, then add/sub", which is what lets every
+// intermediate value stay lazy (see field.cuh).  The function computed is exactly that of
+// NTTReference::compute_forward / compute_inverse (tests/ntt-reference.hpp:43-83): same
+// bit-reversed order, canonical outputs.
+#pragma once
+#if !defined(XNTT_HOST_EMU)
+#include <cuda_runtime.h>
+#endif
+
+#include <cstdint>
+#include <utility>
+
+#include "field.cuh"
+#include "params.h"
+
+namespace xntt {
+
+template <int LOGN>
+struct Stages {
+  static constexpr int kRem = LOGN % 3;
+  static constexpr int LOGR1 = LOGN <= 4 ? LOGN : (kRem == 0 ? 3 : (kRem == 1 ? 4 : 2));
+  static constexpr int NS = 1 + (LOGN - LOGR1) / 3;
+};
+
+template <int C>
+struct Slot;
+template <>
+struct Slot<1> {
+  typedef u64 type;
+  static constexpr int kSwzMask = 15;
+};
+template <>
+struct Slot<2> {
+  typedef ulonglong2 type;
+  static constexpr int kSwzMask = 7;
+};
+
+template <int C>
+__device__ __forceinline__ int swz(int k) {
+  return k ^ ((k >> 3) & Slot<C>::kSwzMask);
+}
+
+template <int LOGN_, int LOGW_, int C_, bool COL_>
+struct PassCfg {
+  static constexpr int LOGN = LOGN_, LOGW = LOGW_, C = C_;
+  static constexpr bool COL = COL_;
+  static constexpr int N = 1 << LOGN, W = 1 << LOGW;
+  static constexpr int NP = W / C;  // column groups per tile
+  static constexpr int LOGNP = LOGW - (C == 2 ? 1 : 0);
+  static constexpr int LOGR1 = Stages<LOGN>::LOGR1;
+  static constexpr int NS = Stages<LOGN>::NS;
+  static constexpr size_t kSmemBytes = NS > 1 ? (size_t)N * W * sizeof(u64) : 0;
+  static_assert(W >= C, "tile narrower than a column group");
+};
+
+template <class Cfg>
+__device__ __forceinline__ int slot_index(int k, int p) {
+  if constexpr (Cfg::COL)
+    return (swz<Cfg::C>(k) << Cfg::LOGNP) + p;
+  else
+    return (p << Cfg::LOGN) + swz<Cfg::C>(k);
+}
+
+template <class Cfg, int R>
+__device__ __forceinline__ void smem_load(const typename Slot<Cfg::C>::type* sm, int k0, int logs, int p,
+                                          u64 (&x)[R][Cfg::C]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    auto v = sm[slot_index<Cfg>(k0 + (r << logs), p)];
+    if constexpr (Cfg::C == 2) {
+      x[r][0] = v.x;
+      x[r][1] = v.y;
+    } else {
+      x[r][0] = v;
+    }
+  }
+}
+
+template <class Cfg, int R>
+__device__ __forceinline__ void smem_store(typename Slot<Cfg::C>::type* sm, int k0, int logs, int p,
+                                           const u64 (&x)[R][Cfg::C]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if constexpr (Cfg::C == 2) {
+      sm[slot_index<Cfg>(k0 + (r << logs), p)] = make_ulonglong2(x[r][0], x[r][1]);
+    } else {
+      sm[slot_index<Cfg>(k0 + (r << logs), p)] = x[r][0];
+    }
+  }
+}
+
+// Global addressing of element (k, column group p, lane c) relative to the tile base.
+template <class Cfg>
+__device__ __forceinline__ u64 gofs(const PassParams& prm, int k, int p, int c) {
+  if constexpr (Cfg::COL)
+    return (u64)k * prm.inner + (u64)(p * Cfg::C + c);
+  else
+    return ((u64)(p * Cfg::C + c) << Cfg::LOGN) + (u64)k;
+}
+
+template <class Cfg, int R>
+__device__ __forceinline__ void gmem_load(const PassParams& prm, const u64* base, u32 row0, int k0, int logs,
+                                          int p, u64 (&x)[R][Cfg::C]) {
+  if constexpr (Cfg::COL) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int k = k0 + (r << logs);
+      if constexpr (Cfg::C == 2) {
+        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(base + gofs<Cfg>(prm, k, p, 0));
+        x[r][0] = v.x;
+        x[r][1] = v.y;
+      } else {
+        x[r][0] = base[gofs<Cfg>(prm, k, p, 0)];
+      }
+    }
+  } else {
+    // row mode: the last tile may hold fewer than W rows
+#pragma unroll
+    for (int c = 0; c < Cfg::C; ++c) {
+      const bool ok = row0 + (u32)(p * Cfg::C + c) < prm.rows;
+#pragma unroll
+      for (int r = 0; r < R; ++r) x[r][c] = ok ? base[gofs<Cfg>(prm, k0 + (r << logs), p, c)] : 0ull;
+    }
+  }
+}
+
+template <class Cfg, int R>
+__device__ __forceinline__ void gmem_store(const PassParams& prm, u64* base, u32 row0, int k0, int logs, int p,
+                                           const u64 (&x)[R][Cfg::C]) {
+  if constexpr (Cfg::COL) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if constexpr (Cfg::C == 2)
+        *reinterpret_cast<ulonglong2*>(base + gofs<Cfg>(prm, k0 + (r << logs), p, 0)) =
+            make_ulonglong2(x[r][0], x[r][1]);
+      else
+        base[gofs<Cfg>(prm, k0 + (r << logs), p, 0)] = x[r][0];
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < Cfg::C; ++c) {
+      if (row0 + (u32)(p * Cfg::C + c) < prm.rows) {
+        if (logs == 0 && R >= 2) {
+          // a thread owns R consecutive outputs of this row: 128-bit stores
+#pragma unroll
+          for (int r = 0; r + 1 < R; r += 2)
+            *reinterpret_cast<ulonglong2*>(base + gofs<Cfg>(prm, k0 + r, p, c)) =
+                make_ulonglong2(x[r][c], x[r + 1][c]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) base[gofs<Cfg>(prm, k0 + (r << logs), p, c)] = x[r][c];
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ Tw ld_tw(const Tw* t) {
+  ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(t));
+  Tw r;
+  r.w = v.x;
+  r.wp = v.y;
+  return r;
+}
+
+// Six-step twiddle of element (k, global column col): omega_M^(bitrev_LOGN(k) * col), looked up as
+// hi[e >> shift] * lo[e & mask] and applied as two Montgomery products (canonical result).
+template <class F, int LOGN>
+__device__ __forceinline__ u64 apply_twist(const PassParams& prm, u64 v, int k, u32 col) {
+  const u32 e = (__brev((u32)k) >> (32 - LOGN)) * col;
+  const Tw lo = ld_tw(prm.twist_lo + (e & ((1u << prm.twist_shift) - 1u)));
+  const Tw hi = ld_tw(prm.twist_hi + (e >> prm.twist_shift));
+  return F::mont(F::mont(v, hi), lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward radix-R register network (Cooley-Tukey, block-indexed twiddles).
+template <class F, int LOGR, int C, bool FIRST>
+__device__ __forceinline__ void fwd_network(u64 (&x)[1 << LOGR][C], const Tw* __restrict__ G, int B) {
+  constexpr int R = 1 << LOGR;
+#pragma unroll
+  for (int lam = 0; lam < LOGR; ++lam) {
+    const int h = R >> (lam + 1);
+#pragma unroll
+    for (int g = 0; g < (1 << lam); ++g) {
+      if (FIRST && g == 0) {
+        // omega = 1.  Level 0 sees canonical input; deeper levels must canonicalise x1 first.
+#pragma unroll
+        for (int r0 = 0; r0 < h; ++r0)
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            if (lam > 0) x[r0 + h][c] = F::canon(x[r0 + h][c]);
+            F::ct_butterfly_one(x[r0][c], x[r0 + h][c]);
+          }
+      } else {
+        const Tw t = ld_tw(G + ((B << lam) + g));
+#pragma unroll
+        for (int r0 = 0; r0 < h; ++r0)
+#pragma unroll
+          for (int c = 0; c < C; ++c) F::ct_butterfly(x[g * 2 * h + r0][c], x[g * 2 * h + r0 + h][c], t);
+      }
+    }
+  }
+}
+
+// Inverse radix-R register network (decimation in time, position-indexed twiddles).
+// Level lam pairs (r, r + 2^lam); element stride is S, task offset inside its block is i.
+template <class F, int LOGR, int C, bool FIRST>
+__device__ __forceinline__ void inv_network(u64 (&x)[1 << LOGR][C], const Tw* __restrict__ I, int logs, int i) {
+  constexpr int R = 1 << LOGR;
+#pragma unroll
+  for (int lam = 0; lam < LOGR; ++lam) {
+    const int h = 1 << lam;
+#pragma unroll
+    for (int j = 0; j < h; ++j) {
+      if (FIRST && j == 0) {
+        // first stage has S = 1, i = 0: position 0 -> omega = 1
+#pragma unroll
+        for (int r = j; r < R; r += 2 * h)
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            if (lam > 0) x[r + h][c] = F::canon(x[r + h][c]);
+            F::ct_butterfly_one(x[r][c], x[r + h][c]);
+          }
+      } else {
+        const Tw t = ld_tw(I + ((h << logs) + i + (j << logs)));
+#pragma unroll
+        for (int r = j; r < R; r += 2 * h)
+#pragma unroll
+          for (int c = 0; c < C; ++c) F::ct_butterfly(x[r][c], x[r + h][c], t);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class F, class Cfg, bool TWIST, int J>
+__device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
+                                          const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
+  constexpr int NS = Cfg::NS;
+  constexpr int LOGR = (J == 0) ? Cfg::LOGR1 : 3;
+  constexpr int R = 1 << LOGR;
+  constexpr int LOGS = 3 * (NS - 1 - J);
+  constexpr int LOGT = Cfg::LOGN - LOGR;  // tasks per sub-transform
+  constexpr int NTASK = (1 << LOGT) * Cfg::NP;
+#pragma unroll 1
+  for (int task = threadIdx.x; task < NTASK; task += kThreads) {
+    int p, t;
+    if constexpr (Cfg::COL) {
+      p = task & (Cfg::NP - 1);
+      t = task >> Cfg::LOGNP;
+    } else {
+      p = task >> LOGT;
+      t = task & ((1 << LOGT) - 1);
+    }
+    const int B = t >> LOGS, i = t & ((1 << LOGS) - 1);
+    const int k0 = (B << (LOGS + LOGR)) + i;
+    u64 x[R][Cfg::C];
+    if constexpr (J == 0)
+      gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
+    else
+      smem_load<Cfg, R>(sm, k0, LOGS, p, x);
+    fwd_network<F, LOGR, Cfg::C, J == 0>(x, prm.tw, B);
+    if constexpr (J == NS - 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < Cfg::C; ++c) {
+          if constexpr (TWIST)
+            x[r][c] = apply_twist<F, Cfg::LOGN>(prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
+          else
+            x[r][c] = F::canon(x[r][c]);
+        }
+      gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
+    } else {
+      smem_store<Cfg, R>(sm, k0, LOGS, p, x);
+    }
+  }
+  if constexpr (J != NS - 1) __syncthreads();
+}
+
+template <class F, class Cfg, bool TWIST, int J>
+__device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
+                                          const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
+  constexpr int NS = Cfg::NS;
+  // inverse stage J mirrors forward stage NS-1-J
+  constexpr int LOGR = (J == NS - 1) ? Cfg::LOGR1 : 3;
+  constexpr int R = 1 << LOGR;
+  constexpr int LOGS = 3 * J;
+  constexpr int LOGT = Cfg::LOGN - LOGR;
+  constexpr int NTASK = (1 << LOGT) * Cfg::NP;
+#pragma unroll 1
+  for (int task = threadIdx.x; task < NTASK; task += kThreads) {
+    int p, t;
+    if constexpr (Cfg::COL) {
+      p = task & (Cfg::NP - 1);
+      t = task >> Cfg::LOGNP;
+    } else {
+      p = task >> LOGT;
+      t = task & ((1 << LOGT) - 1);
+    }
+    const int B = t >> LOGS, i = t & ((1 << LOGS) - 1);
+    const int k0 = (B << (LOGS + LOGR)) + i;
+    u64 x[R][Cfg::C];
+    if constexpr (J == 0) {
+      gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
+      if constexpr (TWIST) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < Cfg::C; ++c)
+            x[r][c] = apply_twist<F, Cfg::LOGN>(prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
+      }
+    } else {
+      smem_load<Cfg, R>(sm, k0, LOGS, p, x);
+    }
+    inv_network<F, LOGR, Cfg::C, J == 0>(x, prm.tw, LOGS, i);
+    if constexpr (J == NS - 1) {
+      if (prm.scale_on) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < Cfg::C; ++c) x[r][c] = F::mont(x[r][c], prm.scale);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < Cfg::C; ++c) x[r][c] = F::canon(x[r][c]);
+      }
+      gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
+    } else {
+      smem_store<Cfg, R>(sm, k0, LOGS, p, x);
+    }
+  }
+  if constexpr (J != NS - 1) __syncthreads();
+}
+
+template <class F, class Cfg, bool INVERSE, bool TWIST, int... Js>
+__device__ __forceinline__ void run_stages(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
+                                           const u64* gsrc, u64* gdst, u32 col0, u32 row0,
+                                           std::integer_sequence<int, Js...>) {
+  if constexpr (INVERSE)
+    (inv_stage<F, Cfg, TWIST, Js>(prm, sm, gsrc, gdst, col0, row0), ...);
+  else
+    (fwd_stage<F, Cfg, TWIST, Js>(prm, sm, gsrc, gdst, col0, row0), ...);
+}
+
+#if !defined(XNTT_HOST_EMU)
+template <class F, int LOGN, int LOGW, int C, bool COL, bool INVERSE, bool TWIST>
+__global__ void __launch_bounds__(kThreads, 2) pass_kernel(const __grid_constant__ PassParams prm) {
+  typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto* sm = reinterpret_cast<typename Slot<C>::type*>(smem_raw);
+  const u32 tile = blockIdx.x;
+  u64 base;
+  u32 col0 = 0, row0 = 0;
+  if constexpr (COL) {
+    const u32 o = tile / prm.tiles_per_outer, cb = tile - o * prm.tiles_per_outer;
+    base = (u64)o * prm.outer_stride + (u64)cb * Cfg::W;
+    col0 = prm.twist_col0 + cb * Cfg::W;
+  } else {
+    base = ((u64)tile << (LOGN + LOGW));
+    row0 = tile << LOGW;
+  }
+  run_stages<F, Cfg, INVERSE, TWIST>(prm, sm, prm.src + base, prm.dst + base, col0, row0,
+                                     std::make_integer_sequence<int, Cfg::NS>{});
+}
+
+#endif  // !XNTT_HOST_EMU
+
+}  // namespace xntt

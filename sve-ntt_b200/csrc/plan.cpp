@@ -1,0 +1,526 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// Planner and C ABI (include/xntt.h).  Pure C++: everything device-side goes through backend.h, so
+// this file is compiled unchanged into libxntt.so (CUDA back-end) and into the host emulator used
+// by the CPU test-suite.  It plays the role of the reference's wrapper + kernel composition
+// (include/sventt/wrapper.hpp:13-83, kernel/recursive.hpp:15-145, kernel/iterative.hpp:17-107):
+// a transform of length m = 2^L is lowered to one, two or three "passes" (pass_kernel.cuh).
+//
+// Decomposition (forward order), m = n0 * n1 [* n2], data viewed row-major [n0][n1][n2]:
+//   pass i < last : column pass of length n_i over stride n_{i+1}*..., fused with the six-step
+//                   twiddle omega_M^(bitrev(k) * col), M = n_i * inner
+//                   (GenericSVELayer::twiddle_rows_forward, layer/sve/generic.hpp:169-268)
+//   last pass     : row pass of length n_last on contiguous rows
+// The output order is the global bit reversal, identical to NTTReference.
+// The inverse runs the same passes backwards with inverse tables; 1/inverse_factor is folded into
+// the outermost pass's twiddle table (or applied at the end of a single-pass inverse).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/xntt.h"
+#include "backend.h"
+#include "field_host.h"
+
+using namespace xntt;
+
+struct PassDesc {
+  int logn = 0;
+  bool col = false;
+  int log_inner = 0;  // column mode: log2 of the distance between consecutive k (unsharded)
+  int log_outer = 0;  // log2 of the number of independent [N][inner] blocks per transform
+  int twist_shift = 0;
+  const Tw* fwd_tw = nullptr;
+  const Tw* inv_tw = nullptr;
+  const Tw* fwd_lo = nullptr;
+  const Tw* fwd_hi = nullptr;
+  const Tw* inv_lo = nullptr;
+  const Tw* inv_hi = nullptr;
+};
+
+struct xntt_plan {
+  xntt_desc desc{};
+  int device = 0;
+  int log2_m = 0;
+  u32 batch = 1;
+  bool fwd = true, inv = true;
+  std::vector<PassDesc> passes;  // forward execution order; the last one is the row pass
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  Tw scale{};  // Montgomery pair of inverse_factor^-1
+  bool scale_on = false;
+  u64 r2 = 0;  // 2^128 mod p
+  u32 shard_count = 1, shard_rank = 0;
+};
+
+namespace {
+
+thread_local std::string g_err = "no error";
+
+int be_fail(int rc) {
+  g_err = be::last_error();
+  return rc == 2 ? XNTT_ERR_ALLOC : XNTT_ERR_CUDA;
+}
+#define BE(call)                       \
+  do {                                 \
+    int rc_ = (call);                  \
+    if (rc_ != 0) return be_fail(rc_); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (be::get_device(&prev) != 0) {
+      ok = false;
+      prev = -1;
+      return;
+    }
+    if (prev != dev && be::set_device(dev) != 0) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) be::set_device(prev);
+  }
+};
+
+int choose_splits(int L, std::vector<int>& out) {
+  out.clear();
+  if (L <= kMaxRowLog) {
+    out.push_back(L);
+  } else if (L <= 24) {
+    int l1 = L - 8 > 12 ? 12 : L - 8;  // prefer a 2^12 row pass (four clean radix-8 stages)
+    if (l1 < L / 2) l1 = L / 2;
+    int l0 = L - l1;
+    if (l0 > 11) {  // keep column tiles at least 4 columns (32 bytes) wide
+      l0 = 11;
+      l1 = L - l0;
+    }
+    out.push_back(l0);
+    out.push_back(l1);
+  } else if (L <= 31) {
+    const int l2 = 12, rest = L - l2;
+    out.push_back((rest + 1) / 2);
+    out.push_back(rest / 2);
+    out.push_back(l2);
+  } else {
+    return XNTT_ERR_INVALID;
+  }
+  return XNTT_OK;
+}
+
+int gen_table(Tw* out, u32 count, int kind, int logn, int shift, u64 root, u64 scale_plain, u64 p) {
+  PowTable t;
+  u64 r = root;
+  for (int i = 0; i < 32; ++i) {
+    t.sq[i] = h_to_mont(r, p);
+    r = h_mul(r, r, p);
+  }
+  t.scale = h_to_mont(scale_plain % p, p);
+  BE(be::launch_gen_table(out, count, kind, logn, shift, t, nullptr));
+  return XNTT_OK;
+}
+
+// One pass.  `count_override` (when non-zero) replaces the number of outer blocks / rows: the row
+// half of a sharded plan only holds 1/shard_count of them.
+int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* src, void* st,
+             u64 count_override) {
+  const PassDesc& ps = pl->passes[i];
+  PassParams prm{};
+  prm.src = src;
+  prm.dst = dst;
+  prm.tw = inverse ? ps.inv_tw : ps.fwd_tw;
+  prm.scale = pl->scale;
+  const int logw = tile_logw(ps.logn);
+  unsigned grid;
+  if (ps.col) {
+    const bool sharded_first = (i == 0 && pl->shard_count > 1);
+    const u64 inner_full = 1ull << ps.log_inner;
+    const u64 inner = sharded_first ? inner_full / pl->shard_count : inner_full;
+    const u64 outer = count_override ? count_override : ((u64)pl->batch << ps.log_outer);
+    prm.inner = inner;
+    prm.outer_stride = inner << ps.logn;
+    prm.tiles_per_outer = (u32)(inner >> logw);
+    prm.twist_lo = inverse ? ps.inv_lo : ps.fwd_lo;
+    prm.twist_hi = inverse ? ps.inv_hi : ps.fwd_hi;
+    prm.twist_shift = (u32)ps.twist_shift;
+    prm.twist_col0 = sharded_first ? (u32)(inner * pl->shard_rank) : 0u;
+    const u64 tiles = outer * prm.tiles_per_outer;
+    if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
+    grid = (unsigned)tiles;
+  } else {
+    const u64 rows = count_override ? count_override : ((u64)pl->batch << (pl->log2_m - ps.logn));
+    if (rows == 0 || rows > 0xffffffffull) return XNTT_ERR_INVALID;
+    prm.rows = (u32)rows;
+    prm.scale_on = (inverse && pl->scale_on && pl->passes.size() == 1) ? 1u : 0u;
+    grid = (unsigned)((rows + (1u << logw) - 1) >> logw);
+  }
+  BE(be::launch_pass(ps.logn, ps.col, inverse, prm, grid, st));
+  return XNTT_OK;
+}
+
+// passes [first, last) in forward order (reverse order for the inverse); the first executed pass
+// reads src, every later one works in place on dst.
+int run_range(const xntt_plan* pl, bool inverse, size_t first, size_t last, u64* dst, const u64* src, void* st,
+              bool shard_rows) {
+  if (!dst || !src) return XNTT_ERR_INVALID;
+  if (inverse ? !pl->inv : !pl->fwd) return XNTT_ERR_STATE;
+  DeviceGuard g(pl->device);
+  if (!g.ok) return be_fail(1);
+  const u64* cur = src;
+  for (size_t s = 0; s < last - first; ++s) {
+    const size_t i = inverse ? last - 1 - s : first + s;
+    u64 count = 0;
+    if (shard_rows) {
+      const PassDesc& ps = pl->passes[i];
+      const u64 full = ps.col ? ((u64)pl->batch << ps.log_outer) : ((u64)pl->batch << (pl->log2_m - ps.logn));
+      count = full / pl->shard_count;
+    }
+    const int rc = run_pass(pl, i, inverse, dst, cur, st, count);
+    if (rc != XNTT_OK) return rc;
+    cur = dst;
+  }
+  return XNTT_OK;
+}
+
+int host_roundtrip(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, bool inverse) {
+  if (!pl || !dst || !src) return XNTT_ERR_INVALID;
+  if (pl->shard_count > 1) return XNTT_ERR_STATE;
+  DeviceGuard g(pl->device);
+  if (!g.ok) return be_fail(1);
+  const size_t bytes = (sizeof(u64) << pl->log2_m) * pl->batch;
+  void* d = nullptr;
+  BE(be::dev_malloc(&d, bytes));
+  int rc = XNTT_OK, brc;
+  if ((brc = be::memcpy_h2d(d, src, bytes, nullptr)) != 0) rc = be_fail(brc);
+  if (rc == XNTT_OK) rc = run_range(pl, inverse, 0, pl->passes.size(), (u64*)d, (const u64*)d, nullptr, false);
+  if (rc == XNTT_OK && (brc = be::memcpy_d2h(dst, d, bytes, nullptr)) != 0) rc = be_fail(brc);
+  brc = be::stream_sync(nullptr);
+  if (rc == XNTT_OK && brc != 0) rc = be_fail(brc);
+  be::dev_free(d);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
+  if (!out || !d) return XNTT_ERR_INVALID;
+  *out = nullptr;
+  if (d->log2_m < 1 || d->log2_m > 31) return XNTT_ERR_INVALID;
+  const u64 p = d->modulus, gen = d->generator;
+  if ((p & 1) == 0 || p < 3 || gen == 0) return XNTT_ERR_INVALID;
+  if (p != kP0) {
+    // other moduli of Modulus<p, g> are SURVEY section 8(f) "next" work
+    return h_is_prime(p) ? XNTT_ERR_UNSUPPORTED : XNTT_ERR_INVALID;
+  }
+  const u64 m = 1ull << d->log2_m;
+  if ((p - 1) % m != 0) return XNTT_ERR_INVALID;  // Modulus::get_root_forward: invalid_argument
+  const u64 root_m = h_pow(gen % p, (p - 1) / m, p);
+  // g must generate the order-m subgroup: omega^(m/2) == -1
+  if (h_pow(root_m, m / 2, p) != p - 1) return XNTT_ERR_INVALID;
+
+  std::vector<int> splits;
+  if (d->n_splits) {
+    if (d->n_splits > XNTT_MAX_SPLITS) return XNTT_ERR_INVALID;
+    u32 sum = 0;
+    for (u32 i = 0; i < d->n_splits; ++i) {
+      splits.push_back((int)d->split_log2[i]);
+      sum += d->split_log2[i];
+    }
+    // IterativeNTT / RecursiveNTT static_assert: the product of the radices equals m
+    if (sum != d->log2_m) return XNTT_ERR_INVALID;
+  } else {
+    const int rc = choose_splits((int)d->log2_m, splits);
+    if (rc != XNTT_OK) return rc;
+  }
+  const u32 shard_count = d->shard_count ? d->shard_count : 1;
+  if (shard_count & (shard_count - 1)) return XNTT_ERR_INVALID;
+  int shard_log = 0;
+  while ((1u << shard_log) < shard_count) ++shard_log;
+  if (shard_count > 1) {
+    if (splits.size() < 2 || d->shard_rank >= shard_count || splits[0] < shard_log) return XNTT_ERR_INVALID;
+  }
+  {
+    int rem = (int)d->log2_m;
+    for (size_t i = 0; i < splits.size(); ++i) {
+      const int l = splits[i];
+      rem -= l;
+      const bool last = i + 1 == splits.size();
+      if (l < 1) return XNTT_ERR_INVALID;
+      if (l > (last ? kMaxRowLog : kMaxColLog)) return XNTT_ERR_UNSUPPORTED;
+      if (!last) {
+        const int log_inner = rem - (i == 0 ? shard_log : 0);
+        if (log_inner < tile_logw(l)) return XNTT_ERR_UNSUPPORTED;  // tile wider than the matrix
+      }
+    }
+  }
+
+  // inverse scaling factor
+  u64 f = d->inverse_factor == 0 ? 1 : d->inverse_factor % p;
+  if (f == 0) return XNTT_ERR_INVALID;
+
+  xntt_plan* pl = new (std::nothrow) xntt_plan;
+  if (!pl) return XNTT_ERR_ALLOC;
+  pl->desc = *d;
+  pl->log2_m = (int)d->log2_m;
+  pl->batch = d->batch ? d->batch : 1;
+  const u32 flags = d->flags ? d->flags : (XNTT_ENABLE_FORWARD | XNTT_ENABLE_INVERSE);
+  pl->fwd = (flags & XNTT_ENABLE_FORWARD) != 0;
+  pl->inv = (flags & XNTT_ENABLE_INVERSE) != 0;
+  pl->shard_count = shard_count;
+  pl->shard_rank = d->shard_rank;
+  const u64 finv = h_inv(f, p);
+  pl->scale_on = (f != 1);
+  pl->scale.w = h_to_mont(finv, p);
+  pl->scale.wp = pl->scale.w * h_montgomery_inverse(p);
+  pl->r2 = h_to_mont(h_to_mont(1, p), p);
+
+  int dev = d->device;
+  if (dev < 0) {
+    const int rc = be::get_device(&dev);
+    if (rc != 0) {
+      delete pl;
+      return be_fail(rc);
+    }
+  }
+  pl->device = dev;
+  DeviceGuard g(dev);
+  if (!g.ok) {
+    delete pl;
+    return be_fail(1);
+  }
+
+  // arena layout (Tw units)
+  const size_t q = splits.size();
+  pl->passes.resize(q);
+  size_t words = 0;
+  std::vector<size_t> off_fwd(q), off_inv(q), off_flo(q), off_fhi(q), off_ilo(q), off_ihi(q);
+  {
+    int rem = pl->log2_m, before = 0;
+    for (size_t i = 0; i < q; ++i) {
+      PassDesc& ps = pl->passes[i];
+      ps.logn = splits[i];
+      rem -= ps.logn;
+      ps.col = i + 1 < q;
+      ps.log_inner = rem;
+      ps.log_outer = before;
+      before += ps.logn;
+      const size_t n = 1ull << ps.logn;
+      off_fwd[i] = words;
+      words += n / 2 ? n / 2 : 1;
+      off_inv[i] = words;
+      words += n;
+      if (ps.col) {
+        const int lm = ps.logn + ps.log_inner;
+        ps.twist_shift = (lm + 1) / 2;
+        const size_t nlo = 1ull << ps.twist_shift, nhi = 1ull << (lm - ps.twist_shift);
+        off_flo[i] = words;
+        words += nlo;
+        off_fhi[i] = words;
+        words += nhi;
+        off_ilo[i] = words;
+        words += nlo;
+        off_ihi[i] = words;
+        words += nhi;
+      }
+    }
+  }
+  pl->arena_bytes = words * sizeof(Tw);
+  {
+    const int rc = be::dev_malloc(&pl->arena, pl->arena_bytes);
+    if (rc != 0) {
+      delete pl;
+      g_err = be::last_error();
+      return XNTT_ERR_ALLOC;
+    }
+  }
+  Tw* base = static_cast<Tw*>(pl->arena);
+  int rc = XNTT_OK;
+  for (size_t i = 0; i < q && rc == XNTT_OK; ++i) {
+    PassDesc& ps = pl->passes[i];
+    const u64 n = 1ull << ps.logn;
+    const u64 root_n = h_pow(gen % p, (p - 1) / n, p);
+    ps.fwd_tw = base + off_fwd[i];
+    ps.inv_tw = base + off_inv[i];
+    rc = gen_table(base + off_fwd[i], (u32)(n / 2 ? n / 2 : 1), kFwdG, ps.logn, 0, root_n, 1, p);
+    if (rc == XNTT_OK) rc = gen_table(base + off_inv[i], (u32)n, kInvI, ps.logn, 0, h_inv(root_n, p), 1, p);
+    if (ps.col && rc == XNTT_OK) {
+      const int lm = ps.logn + ps.log_inner;
+      const u64 root_big = h_pow(gen % p, (p - 1) >> lm, p);
+      const u64 root_big_inv = h_inv(root_big, p);
+      const u32 nlo = 1u << ps.twist_shift, nhi = 1u << (lm - ps.twist_shift);
+      ps.fwd_lo = base + off_flo[i];
+      ps.fwd_hi = base + off_fhi[i];
+      ps.inv_lo = base + off_ilo[i];
+      ps.inv_hi = base + off_ihi[i];
+      rc = gen_table(base + off_flo[i], nlo, kPowers, 0, 0, root_big, 1, p);
+      if (rc == XNTT_OK) rc = gen_table(base + off_fhi[i], nhi, kPowers, 0, ps.twist_shift, root_big, 1, p);
+      if (rc == XNTT_OK) rc = gen_table(base + off_ilo[i], nlo, kPowers, 0, 0, root_big_inv, 1, p);
+      // the outermost column pass runs last in the inverse: fold 1/inverse_factor into its table
+      if (rc == XNTT_OK)
+        rc = gen_table(base + off_ihi[i], nhi, kPowers, 0, ps.twist_shift, root_big_inv, i == 0 ? finv : 1, p);
+    }
+  }
+  if (rc == XNTT_OK) {
+    const int brc = be::stream_sync(nullptr);
+    if (brc != 0) rc = be_fail(brc);
+  }
+  if (rc != XNTT_OK) {
+    be::dev_free(pl->arena);
+    delete pl;
+    return rc;
+  }
+  *out = pl;
+  return XNTT_OK;
+}
+
+int xntt_plan_destroy(xntt_plan* pl) {
+  if (!pl) return XNTT_OK;
+  if (pl->arena) {
+    DeviceGuard g(pl->device);
+    be::dev_free(pl->arena);
+  }
+  delete pl;
+  return XNTT_OK;
+}
+
+uint64_t xntt_plan_m(const xntt_plan* pl) { return pl ? (1ull << pl->log2_m) : 0; }
+uint32_t xntt_plan_batch(const xntt_plan* pl) { return pl ? pl->batch : 0; }
+uint32_t xntt_plan_launches(const xntt_plan* pl, int) { return pl ? (uint32_t)pl->passes.size() : 0; }
+uint32_t xntt_plan_splits(const xntt_plan* pl, uint32_t* out, uint32_t n) {
+  if (!pl) return 0;
+  for (uint32_t i = 0; out && i < n && i < pl->passes.size(); ++i) out[i] = (uint32_t)pl->passes[i].logn;
+  return (uint32_t)pl->passes.size();
+}
+
+int xntt_forward(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* stream) {
+  if (!pl) return XNTT_ERR_INVALID;
+  if (pl->shard_count > 1) return XNTT_ERR_STATE;
+  return run_range(pl, false, 0, pl->passes.size(), (u64*)dst, (const u64*)src, stream, false);
+}
+int xntt_inverse(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* stream) {
+  if (!pl) return XNTT_ERR_INVALID;
+  if (pl->shard_count > 1) return XNTT_ERR_STATE;
+  return run_range(pl, true, 0, pl->passes.size(), (u64*)dst, (const u64*)src, stream, false);
+}
+
+int xntt_shard_forward_cols(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* stream) {
+  if (!pl || pl->shard_count < 2) return XNTT_ERR_STATE;
+  return run_range(pl, false, 0, 1, (u64*)dst, (const u64*)src, stream, false);
+}
+int xntt_shard_forward_rows(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* stream) {
+  if (!pl || pl->shard_count < 2) return XNTT_ERR_STATE;
+  return run_range(pl, false, 1, pl->passes.size(), (u64*)dst, (const u64*)src, stream, true);
+}
+int xntt_shard_inverse_rows(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* stream) {
+  if (!pl || pl->shard_count < 2) return XNTT_ERR_STATE;
+  return run_range(pl, true, 1, pl->passes.size(), (u64*)dst, (const u64*)src, stream, true);
+}
+int xntt_shard_inverse_cols(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* stream) {
+  if (!pl || pl->shard_count < 2) return XNTT_ERR_STATE;
+  return run_range(pl, true, 0, 1, (u64*)dst, (const u64*)src, stream, false);
+}
+
+int xntt_forward_host(const xntt_plan* pl, uint64_t* dst, const uint64_t* src) {
+  return host_roundtrip(pl, dst, src, false);
+}
+int xntt_inverse_host(const xntt_plan* pl, uint64_t* dst, const uint64_t* src) {
+  return host_roundtrip(pl, dst, src, true);
+}
+
+int xntt_to_montgomery(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, size_t n, void* st) {
+  if (!pl || !dst || !src) return XNTT_ERR_INVALID;
+  if (n == 0) return XNTT_OK;
+  DeviceGuard g(pl->device);
+  BE(be::launch_to_mont((u64*)dst, (const u64*)src, n, pl->r2, st));
+  return XNTT_OK;
+}
+int xntt_from_montgomery(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, size_t n, void* st) {
+  if (!pl || !dst || !src) return XNTT_ERR_INVALID;
+  if (n == 0) return XNTT_OK;
+  DeviceGuard g(pl->device);
+  BE(be::launch_from_mont((u64*)dst, (const u64*)src, n, st));
+  return XNTT_OK;
+}
+int xntt_multiply_normalize(const xntt_plan* pl, uint64_t* dst, const uint64_t* a, const uint64_t* b, size_t n,
+                            void* st) {
+  if (!pl || !dst || !a || !b) return XNTT_ERR_INVALID;
+  if (n == 0) return XNTT_OK;
+  DeviceGuard g(pl->device);
+  BE(be::launch_mulnorm((u64*)dst, (const u64*)a, (const u64*)b, n, st));
+  return XNTT_OK;
+}
+
+int xntt_alloc_device(void** ptr, size_t bytes, int device) {
+  if (!ptr) return XNTT_ERR_INVALID;
+  *ptr = nullptr;
+  if (device >= 0) BE(be::set_device(device));
+  BE(be::dev_malloc(ptr, bytes));
+  return XNTT_OK;
+}
+int xntt_free_device(void* ptr) {
+  BE(be::dev_free(ptr));
+  return XNTT_OK;
+}
+int xntt_alloc_pinned(void** ptr, size_t bytes) {
+  if (!ptr) return XNTT_ERR_INVALID;
+  *ptr = nullptr;
+  BE(be::host_malloc_pinned(ptr, bytes));
+  return XNTT_OK;
+}
+int xntt_free_pinned(void* ptr) {
+  BE(be::host_free_pinned(ptr));
+  return XNTT_OK;
+}
+int xntt_memcpy_h2d(void* dst, const void* src, size_t bytes, void* st) {
+  BE(be::memcpy_h2d(dst, src, bytes, st));
+  return XNTT_OK;
+}
+int xntt_memcpy_d2h(void* dst, const void* src, size_t bytes, void* st) {
+  BE(be::memcpy_d2h(dst, src, bytes, st));
+  return XNTT_OK;
+}
+int xntt_stream_synchronize(void* st) {
+  BE(be::stream_sync(st));
+  return XNTT_OK;
+}
+
+const char* xntt_strerror(int s) {
+  switch (s) {
+    case XNTT_OK:
+      return "ok";
+    case XNTT_ERR_INVALID:
+      return "invalid argument";
+    case XNTT_ERR_UNSUPPORTED:
+      return "unsupported configuration";
+    case XNTT_ERR_ALLOC:
+      return "allocation failed";
+    case XNTT_ERR_CUDA:
+      return "CUDA error";
+    case XNTT_ERR_STATE:
+      return "operation not enabled for this plan";
+    default:
+      return "unknown status";
+  }
+}
+const char* xntt_last_cuda_error(void) { return g_err.c_str(); }
+const char* xntt_version(void) { return "xntt 0.1 sm_100a"; }
+int xntt_device_count(void) {
+  int n = 0;
+  const int rc = be::device_count(&n);
+  if (rc != 0) return be_fail(rc);
+  return n;
+}
+
+int xntt_microbench(int kind, int iters, double* gops, double* ms) {
+  if (kind < 0 || kind > 4 || iters <= 0 || !gops) return XNTT_ERR_INVALID;
+  BE(be::microbench(kind, iters, gops, ms));
+  return XNTT_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,172 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// TEST INFRASTRUCTURE ONLY.  A host implementation of sve-ntt_b200/csrc/backend.h that executes
+// the *same* kernel templates (pass_kernel.cuh, misc_kernels.cuh) one emulated CUDA thread at a
+// time.  Linked with the unchanged planner (plan.cpp) it yields libxntt_emu.so, which the
+// `-m "not gpu"` tests compare against the oracle: this covers the planner, the table
+// generation, the stage/twiddle index algebra and the lazy arithmetic identities without a GPU.
+// It is never loaded by the product, by bench.py's timed path or by the -m gpu tests.
+#define XNTT_HOST_EMU 1
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// --- minimal CUDA vocabulary for the kernel templates ---------------------------------------
+struct ulonglong2 {
+  unsigned long long x, y;
+};
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return {x, y}; }
+struct EmuIdx {
+  unsigned x = 0, y = 0, z = 0;
+};
+static thread_local EmuIdx threadIdx, blockIdx;
+static inline void __syncthreads() {}
+template <class T>
+static inline T __ldg(const T* p) {
+  return *p;
+}
+static inline unsigned __brev(unsigned v) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
+  return r;
+}
+#define __restrict__
+#define __global__
+#define __grid_constant__
+
+#include "../../sve-ntt_b200/csrc/backend.h"
+#include "../../sve-ntt_b200/csrc/misc_kernels.cuh"
+#include "../../sve-ntt_b200/csrc/pass_kernel.cuh"
+
+namespace xntt {
+typedef Field<kP0> F0;
+
+template <class Cfg, bool INV, bool TWIST, int J>
+static void emu_stage_all_threads(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc,
+                                  u64* gdst, u32 col0, u32 row0) {
+  for (unsigned t = 0; t < (unsigned)kThreads; ++t) {
+    threadIdx.x = t;
+    if constexpr (INV)
+      inv_stage<F0, Cfg, TWIST, J>(prm, sm, gsrc, gdst, col0, row0);
+    else
+      fwd_stage<F0, Cfg, TWIST, J>(prm, sm, gsrc, gdst, col0, row0);
+  }
+}
+
+template <class Cfg, bool INV, bool TWIST, int... Js>
+static void emu_stages(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc, u64* gdst,
+                       u32 col0, u32 row0, std::integer_sequence<int, Js...>) {
+  // a stage ends with a block-wide barrier: run every emulated thread through stage J, then J + 1
+  (emu_stage_all_threads<Cfg, INV, TWIST, Js>(prm, sm, gsrc, gdst, col0, row0), ...);
+}
+
+template <int LOGN, bool COL, bool INV>
+static int emu_launch(const PassParams& prm, unsigned grid) {
+  constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
+  typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
+  std::vector<typename Slot<C>::type> sm((size_t)Cfg::N * Cfg::NP + 1);
+  for (unsigned tile = 0; tile < grid; ++tile) {
+    // body of pass_kernel()
+    u64 base;
+    u32 col0 = 0, row0 = 0;
+    if constexpr (COL) {
+      const u32 o = tile / prm.tiles_per_outer, cb = tile - o * prm.tiles_per_outer;
+      base = (u64)o * prm.outer_stride + (u64)cb * Cfg::W;
+      col0 = prm.twist_col0 + cb * Cfg::W;
+    } else {
+      base = ((u64)tile << (LOGN + LOGW));
+      row0 = tile << LOGW;
+    }
+    // poison shared memory so that a missing write shows up
+    memset(sm.data(), 0xcd, sm.size() * sizeof(sm[0]));
+    emu_stages<Cfg, INV, COL>(prm, sm.data(), prm.src + base, prm.dst + base, col0, row0,
+                              std::make_integer_sequence<int, Cfg::NS>{});
+  }
+  return 0;
+}
+
+#define EMU_CASE(L)                                                       \
+  case L:                                                                 \
+    if (col)                                                              \
+      return inverse ? emu_launch<L, true, true>(prm, grid) : emu_launch<L, true, false>(prm, grid); \
+    else                                                                  \
+      return inverse ? emu_launch<L, false, true>(prm, grid) : emu_launch<L, false, false>(prm, grid);
+
+namespace be {
+
+static std::string g_err = "no error";
+
+int device_count(int* n) {
+  *n = 1;
+  return 0;
+}
+int get_device(int* dev) {
+  *dev = 0;
+  return 0;
+}
+int set_device(int) { return 0; }
+int dev_malloc(void** p, size_t bytes) {
+  *p = aligned_alloc(64, (bytes + 63) / 64 * 64 + 64);
+  if (!*p) {
+    g_err = "out of memory";
+    return 2;
+  }
+  memset(*p, 0xab, bytes);
+  return 0;
+}
+int dev_free(void* p) {
+  free(p);
+  return 0;
+}
+int host_malloc_pinned(void** p, size_t bytes) { return dev_malloc(p, bytes); }
+int host_free_pinned(void* p) { return dev_free(p); }
+int memcpy_h2d(void* dst, const void* src, size_t bytes, void*) {
+  memmove(dst, src, bytes);
+  return 0;
+}
+int memcpy_d2h(void* dst, const void* src, size_t bytes, void*) {
+  memmove(dst, src, bytes);
+  return 0;
+}
+int stream_sync(void*) { return 0; }
+const char* last_error() { return g_err.c_str(); }
+
+int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void*) {
+  switch (logn) {
+    EMU_CASE(1) EMU_CASE(2) EMU_CASE(3) EMU_CASE(4) EMU_CASE(5) EMU_CASE(6) EMU_CASE(7)
+    EMU_CASE(8) EMU_CASE(9) EMU_CASE(10) EMU_CASE(11) EMU_CASE(12)
+    case 13:
+      if (col) break;
+      return inverse ? emu_launch<13, false, true>(prm, grid) : emu_launch<13, false, false>(prm, grid);
+    default:
+      break;
+  }
+  g_err = "invalid pass length";
+  return 1;
+}
+
+int launch_gen_table(Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t, void*) {
+  for (u32 i = 0; i < count; ++i) out[i] = table_entry<F0>(i, kind, logn, shift, t);
+  return 0;
+}
+int launch_to_mont(u64* dst, const u64* src, size_t n, u64 r2, void*) {
+  const u64 r2p = F0::companion(r2);
+  for (size_t i = 0; i < n; ++i) dst[i] = ew_to_mont<F0>(src[i], r2, r2p);
+  return 0;
+}
+int launch_from_mont(u64* dst, const u64* src, size_t n, void*) {
+  for (size_t i = 0; i < n; ++i) dst[i] = ew_from_mont<F0>(src[i]);
+  return 0;
+}
+int launch_mulnorm(u64* dst, const u64* a, const u64* b, size_t n, void*) {
+  for (size_t i = 0; i < n; ++i) dst[i] = ew_mulnorm<F0>(a[i], b[i]);
+  return 0;
+}
+int microbench(int, int, double*, double*) {
+  g_err = "no device";
+  return 1;
+}
+
+}  // namespace be
+}  // namespace xntt

@@ -1,0 +1,116 @@
+# SPDX-License-Identifier: Apache-2.0
+"""ctypes view of the CPU oracle (oracle/_build/libntt_oracle.so) and, when present, of the
+reference's own oracle class (oracle/_ref/libnttref.so).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libntt_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libnttref.so")
+
+_u64 = C.c_uint64
+_ptr = C.c_void_p
+
+
+def _build_oracle():
+    if not os.path.exists(ORACLE_SO):
+        subprocess.run(["make", "_build/libntt_oracle.so"], cwd=ORACLE_DIR, check=True)
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+class Oracle:
+    def __init__(self):
+        _build_oracle()
+        L = self.lib = C.CDLL(ORACLE_SO)
+        for name, res, args in [
+            ("oracle_mulmod", _u64, [_u64, _u64, _u64]),
+            ("oracle_powmod", _u64, [_u64, _u64, _u64]),
+            ("oracle_addmod", _u64, [_u64, _u64, _u64]),
+            ("oracle_submod", _u64, [_u64, _u64, _u64]),
+            ("oracle_root_forward", _u64, [_u64, _u64, _u64]),
+            ("oracle_root_inverse", _u64, [_u64, _u64, _u64]),
+            ("oracle_montgomery_inverse", _u64, [_u64]),
+            ("oracle_to_montgomery", _u64, [_u64, _u64]),
+            ("oracle_from_montgomery", _u64, [_u64, _u64]),
+            ("oracle_precompute", _u64, [_u64, _u64]),
+            ("oracle_multiply_normalize", _u64, [_u64, _u64, _u64, _u64]),
+            ("oracle_ntt_forward", None, [_ptr, _ptr, _u64, _u64, _u64]),
+            ("oracle_ntt_inverse", None, [_ptr, _ptr, _u64, _u64, _u64]),
+            ("oracle_pointwise_mul", None, [_ptr, _ptr, _ptr, _u64, _u64]),
+            ("oracle_dft_point", _u64, [_ptr, _u64, _u64, _u64, _u64]),
+            ("oracle_fill_xorshift", None, [_ptr, _u64, _u64, _u64]),
+            ("oracle_fnv64", _u64, [_ptr, _u64]),
+        ]:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+
+    def ntt_forward(self, a, N, g):
+        out = np.empty_like(a)
+        self.lib.oracle_ntt_forward(_p(out), _p(a), a.size, N, g)
+        return out
+
+    def ntt_inverse(self, a, N, g):
+        out = np.empty_like(a)
+        self.lib.oracle_ntt_inverse(_p(out), _p(a), a.size, N, g)
+        return out
+
+    def pointwise_mul(self, a, b, N):
+        out = np.empty_like(a)
+        self.lib.oracle_pointwise_mul(_p(out), _p(a), _p(b), a.size, N)
+        return out
+
+    def dft_point(self, a, N, g, pos):
+        return int(self.lib.oracle_dft_point(_p(a), a.size, N, g, pos))
+
+    def fill_xorshift(self, count, seed, N):
+        out = np.empty(count, dtype=np.uint64)
+        self.lib.oracle_fill_xorshift(_p(out), count, seed, N)
+        return out
+
+    def fnv64(self, a):
+        return int(self.lib.oracle_fnv64(_p(a), a.size))
+
+    def __getattr__(self, name):  # scalar helpers: o.mulmod(x, y, N) ...
+        fn = getattr(self.lib, "oracle_" + name)
+        return lambda *args: int(fn(*args))
+
+
+class Reference:
+    """NTTReference / sventt::Modulus compiled from /root/reference (oracle/_ref)."""
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(REF_SO)
+        L = self.lib = C.CDLL(REF_SO)
+        for name, res, args in [
+            ("ref_ntt_forward", None, [_ptr, _ptr, _u64, _u64, _u64]),
+            ("ref_ntt_inverse", None, [_ptr, _ptr, _u64, _u64, _u64]),
+            ("ref_root", _u64, [C.c_int, C.c_int, _u64]),
+            ("ref_montgomery_inverse", _u64, [C.c_int]),
+            ("ref_multiply", _u64, [C.c_int, _u64, _u64]),
+            ("ref_power", _u64, [C.c_int, _u64, _u64]),
+        ]:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+
+    def ntt_forward(self, a, N, g):
+        out = np.empty_like(a)
+        self.lib.ref_ntt_forward(_p(out), _p(a), a.size, N, g)
+        return out
+
+    def ntt_inverse(self, a, N, g):
+        out = np.empty_like(a)
+        self.lib.ref_ntt_inverse(_p(out), _p(a), a.size, N, g)
+        return out
+
+
+def have_reference():
+    return os.path.exists(REF_SO)
