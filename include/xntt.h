@@ -84,6 +84,11 @@ int xntt_forward(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void
 /* sventt::NTT<kernel>::compute_inverse(dst, src) / compute_inverse(dst)  (wrapper.hpp:67-82) */
 int xntt_inverse(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
 
+/* One pass of a plan on its own (profiling / per-kernel timing): pass index in forward order,
+ * inverse != 0 runs the inverse kernel of that pass.  In place or src -> dst like the full calls. */
+int xntt_run_pass(const xntt_plan* plan, uint32_t pass, int inverse, uint64_t* dst, const uint64_t* src,
+                  void* stream);
+
 /* The same two calls on host buffers: H2D copy, transform, D2H copy, synchronise. */
 int xntt_forward_host(const xntt_plan* plan, uint64_t* dst, const uint64_t* src);
 int xntt_inverse_host(const xntt_plan* plan, uint64_t* dst, const uint64_t* src);
@@ -117,6 +122,8 @@ int xntt_free_pinned(void* ptr);
 int xntt_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream);
 int xntt_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes, void* stream);
 int xntt_stream_synchronize(void* stream);
+/* 1 if ptr is device (or managed) memory, 0 if it is ordinary/pinned host memory, < 0 on error */
+int xntt_pointer_is_device(const void* ptr);
 
 const char* xntt_strerror(int status);
 /* last cudaError_t seen by this thread inside the library, as text */
@@ -129,7 +136,8 @@ int xntt_device_count(void);
 /* Micro-benchmarks that calibrate the integer roofline (tools/ and bench.py): run `iters`
  * dependent-free rounds of the named instruction mix in registers on every SM and return the
  * achieved rate in giga-operations per second in *gops.  kind: 0 = IMAD (32-bit mad.lo),
- * 1 = IMAD.WIDE, 2 = IADD3, 3 = Montgomery butterflies (gops = butterflies/s / 1e9). */
+ * 1 = IMAD.WIDE, 2 = IADD3, 3 = Montgomery butterflies (gops = butterflies/s / 1e9), 4 = IMAD and LOP3 interleaved,
+ * 5 = IMAD.HI. */
 int xntt_microbench(int kind, int iters, double* gops, double* ms);
 
 #ifdef __cplusplus

@@ -55,6 +55,7 @@ SYMBOLS = {
     "xntt_plan_splits": (C.c_uint32, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
     "xntt_forward": (C.c_int, [_P, _U64P, _U64P, _P]),
     "xntt_inverse": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_run_pass": (C.c_int, [_P, C.c_uint32, C.c_int, _U64P, _U64P, _P]),
     "xntt_forward_host": (C.c_int, [_P, _U64P, _U64P]),
     "xntt_inverse_host": (C.c_int, [_P, _U64P, _U64P]),
     "xntt_shard_forward_cols": (C.c_int, [_P, _U64P, _U64P, _P]),
@@ -71,6 +72,7 @@ SYMBOLS = {
     "xntt_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "xntt_memcpy_d2h": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "xntt_stream_synchronize": (C.c_int, [_P]),
+    "xntt_pointer_is_device": (C.c_int, [_P]),
     "xntt_strerror": (C.c_char_p, [C.c_int]),
     "xntt_last_cuda_error": (C.c_char_p, []),
     "xntt_version": (C.c_char_p, []),
@@ -170,6 +172,9 @@ class Plan:
 
     def inverse(self, dst, src, stream=0):
         self._call("xntt_inverse", dst, src, stream)
+
+    def run_pass(self, index, inverse, dst, src, stream=0):
+        self._call("xntt_run_pass", index, 1 if inverse else 0, dst, src, stream)
 
     def forward_host(self, dst, src):
         self._call("xntt_forward_host", dst, src)

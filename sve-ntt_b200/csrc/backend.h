@@ -20,6 +20,7 @@ int host_free_pinned(void* p);
 int memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
 int memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
 int stream_sync(void* stream);
+int pointer_is_device(const void* p, int* is_device);
 const char* last_error();
 
 int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void* stream);

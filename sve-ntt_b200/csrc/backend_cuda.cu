@@ -109,6 +109,21 @@ __global__ void __launch_bounds__(256) microbench_kernel(u64* out, int iters, u3
 #pragma unroll
     for (int i = 0; i < 8; ++i) s ^= x[i];
     if (s == 0x12345u) out[tid] = s;
+  } else if constexpr (KIND == 5) {
+    u32 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = tid * 0x9e3779b1u + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __umulhi(x[i], a) + b;
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= x[i];
+    if (s == 0x12345u) out[tid] = s;
   } else {
     // IMAD and LOP3 interleaved 1:1 (dual-pipe issue test)
     u32 x[8], y[8];
@@ -172,6 +187,17 @@ int memcpy_d2h(void* dst, const void* src, size_t bytes, void* st) {
 }
 int stream_sync(void* st) {
   CU(cudaStreamSynchronize((cudaStream_t)st));
+  return 0;
+}
+int pointer_is_device(const void* p, int* is_device) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // unregistered host memory on old drivers: not an error for us
+    *is_device = 0;
+    return 0;
+  }
+  *is_device = (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
   return 0;
 }
 const char* last_error() { return g_err.c_str(); }
@@ -240,6 +266,9 @@ int microbench(int kind, int iters, double* gops, double* ms_out) {
         break;
       case 3:
         microbench_kernel<3><<<blocks, threads>>>(out, iters, 0x9e3779b1u, 0x7f4a7c15u);
+        break;
+      case 5:
+        microbench_kernel<5><<<blocks, threads>>>(out, iters, 0x9e3779b1u, 0x7f4a7c15u);
         break;
       default:
         microbench_kernel<4><<<blocks, threads>>>(out, iters, 0x9e3779b1u, 0x7f4a7c15u);

@@ -53,6 +53,7 @@ struct xntt_plan {
   bool scale_on = false;
   u64 r2 = 0;  // 2^128 mod p
   u32 shard_count = 1, shard_rank = 0;
+  mutable void* staging = nullptr;  // device buffer behind the *_host entry points (lazy)
 };
 
 namespace {
@@ -190,15 +191,14 @@ int host_roundtrip(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, bool
   DeviceGuard g(pl->device);
   if (!g.ok) return be_fail(1);
   const size_t bytes = (sizeof(u64) << pl->log2_m) * pl->batch;
-  void* d = nullptr;
-  BE(be::dev_malloc(&d, bytes));
+  if (!pl->staging) BE(be::dev_malloc(&pl->staging, bytes));
+  void* d = pl->staging;
   int rc = XNTT_OK, brc;
   if ((brc = be::memcpy_h2d(d, src, bytes, nullptr)) != 0) rc = be_fail(brc);
   if (rc == XNTT_OK) rc = run_range(pl, inverse, 0, pl->passes.size(), (u64*)d, (const u64*)d, nullptr, false);
   if (rc == XNTT_OK && (brc = be::memcpy_d2h(dst, d, bytes, nullptr)) != 0) rc = be_fail(brc);
   brc = be::stream_sync(nullptr);
   if (rc == XNTT_OK && brc != 0) rc = be_fail(brc);
-  be::dev_free(d);
   return rc;
 }
 
@@ -380,9 +380,10 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
 
 int xntt_plan_destroy(xntt_plan* pl) {
   if (!pl) return XNTT_OK;
-  if (pl->arena) {
+  {
     DeviceGuard g(pl->device);
-    be::dev_free(pl->arena);
+    if (pl->arena) be::dev_free(pl->arena);
+    if (pl->staging) be::dev_free(pl->staging);
   }
   delete pl;
   return XNTT_OK;
@@ -406,6 +407,13 @@ int xntt_inverse(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* 
   if (!pl) return XNTT_ERR_INVALID;
   if (pl->shard_count > 1) return XNTT_ERR_STATE;
   return run_range(pl, true, 0, pl->passes.size(), (u64*)dst, (const u64*)src, stream, false);
+}
+
+int xntt_run_pass(const xntt_plan* pl, uint32_t pass, int inverse, uint64_t* dst, const uint64_t* src,
+                  void* stream) {
+  if (!pl || pass >= pl->passes.size()) return XNTT_ERR_INVALID;
+  if (pl->shard_count > 1) return XNTT_ERR_STATE;
+  return run_range(pl, inverse != 0, pass, pass + 1, (u64*)dst, (const u64*)src, stream, false);
 }
 
 int xntt_shard_forward_cols(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* stream) {
@@ -489,6 +497,12 @@ int xntt_stream_synchronize(void* st) {
   return XNTT_OK;
 }
 
+int xntt_pointer_is_device(const void* ptr) {
+  int k = 0;
+  BE(be::pointer_is_device(ptr, &k));
+  return k;
+}
+
 const char* xntt_strerror(int s) {
   switch (s) {
     case XNTT_OK:
@@ -517,7 +531,7 @@ int xntt_device_count(void) {
 }
 
 int xntt_microbench(int kind, int iters, double* gops, double* ms) {
-  if (kind < 0 || kind > 4 || iters <= 0 || !gops) return XNTT_ERR_INVALID;
+  if (kind < 0 || kind > 5 || iters <= 0 || !gops) return XNTT_ERR_INVALID;
   BE(be::microbench(kind, iters, gops, ms));
   return XNTT_OK;
 }

@@ -130,6 +130,10 @@ int memcpy_d2h(void* dst, const void* src, size_t bytes, void*) {
   return 0;
 }
 int stream_sync(void*) { return 0; }
+int pointer_is_device(const void*, int* is_device) {
+  *is_device = 0;
+  return 0;
+}
 const char* last_error() { return g_err.c_str(); }
 
 int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void*) {

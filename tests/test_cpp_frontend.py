@@ -1,0 +1,34 @@
+# SPDX-License-Identifier: Apache-2.0
+"""The reference's benchmark-as-test (tests/bench-ntt.cpp + tests/ntt-tests/*.hpp) compiled against
+the drop-in C++20 headers (sve-ntt_b200/host/sventt): on the CPU with the host emulator, on the GPU
+with libxntt.so."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+CPP = os.path.join(ROOT, "tests", "cpp")
+
+
+def _build(target):
+    subprocess.run(["make", f"_build/{target}"], cwd=CPP, check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(CPP, "_build", target)
+
+
+def test_reference_compositions_on_emulator():
+    exe = _build("ntt_tests_emu")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ALL OK" in out.stdout and "MISMATCH" not in out.stdout
+    assert out.stdout.count(" ok") == 16
+
+
+@pytest.mark.gpu
+def test_reference_compositions_on_gpu():
+    exe = _build("ntt_tests_gpu")
+    out = subprocess.run([exe, "--big"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ALL OK" in out.stdout and "MISMATCH" not in out.stdout
+    assert out.stdout.count(" ok") == 18

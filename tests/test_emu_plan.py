@@ -1,0 +1,191 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Planner + kernel index algebra on the CPU: the host emulator (tests/emu) executes the same
+kernel templates as the GPU, one emulated thread at a time, and must match the oracle word for
+word.  Mirrors the shapes of the reference's ntt-tests (tests/ntt-tests/*.hpp: 2^5 .. 2^15,
+iterative / recursive / four-step) and the README example (2^17 = 2^8 x 2^9)."""
+import numpy as np
+import pytest
+
+from conftest import G0, P0, SEED
+
+
+def roundtrip(emu, oracle, L, splits=None, batch=1, inverse_factor=None):
+    m = 1 << L
+    a = oracle.fill_xorshift(m * batch, SEED + L, P0)
+    plan = emu.plan(L, splits=splits, batch=batch, inverse_factor=inverse_factor)
+    out = np.empty_like(a)
+    plan.forward(out.ctypes.data, a.ctypes.data)
+    for b in range(batch):
+        want = oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), P0, G0)
+        assert np.array_equal(out[b * m:(b + 1) * m], want), (L, splits, b)
+    back = np.empty_like(a)
+    plan.inverse(back.ctypes.data, out.ctypes.data)
+    f = m if inverse_factor is None else inverse_factor
+    scale = np.full_like(a, (m * pow(f, -1, P0)) % P0)
+    assert np.array_equal(back, oracle.pointwise_mul(a, scale, P0)), (L, splits)
+    inplace = a.copy()
+    plan.forward(inplace.ctypes.data, inplace.ctypes.data)
+    assert np.array_equal(inplace, out)
+    plan.inverse(inplace.ctypes.data, inplace.ctypes.data)
+    assert np.array_equal(inplace, back)
+    return plan.splits
+
+
+@pytest.mark.parametrize("L", range(1, 14))
+def test_single_pass_sizes(emu, oracle, L):
+    assert roundtrip(emu, oracle, L) == [L]
+
+
+@pytest.mark.parametrize("L", [14, 15, 16, 17, 18, 20])
+def test_default_two_pass(emu, oracle, L):
+    assert len(roundtrip(emu, oracle, L)) == 2
+
+
+@pytest.mark.parametrize("L,splits", [
+    (17, [8, 9]),    # README.md:28-68  blocked six-step 2^8 x 2^9
+    (13, [9, 4]),    # ntt-tests/recursive-scalar-fourstep-two13.hpp
+    (15, [9, 6]),    # ntt-tests/recursive-sve-fourstep-two13.hpp (m = 2^15)
+    (13, [1, 12]), (14, [12, 2]), (10, [5, 5]), (16, [5, 5, 6]), (18, [6, 6, 6]), (13, [4, 4, 5]),
+])
+def test_explicit_splits(emu, oracle, L, splits):
+    assert roundtrip(emu, oracle, L, splits=splits) == splits
+
+
+@pytest.mark.parametrize("L,batch", [(3, 1), (3, 33), (6, 5), (10, 7), (12, 3), (13, 2), (15, 3)])
+def test_batches_including_ragged_tiles(emu, oracle, L, batch):
+    roundtrip(emu, oracle, L, batch=batch)
+
+
+@pytest.mark.parametrize("L,splits", [(9, None), (12, None), (14, None), (16, [5, 5, 6])])
+def test_inverse_factor_variants(emu, oracle, L, splits):
+    roundtrip(emu, oracle, L, splits=splits, inverse_factor=1)       # README example: unscaled inverse
+    roundtrip(emu, oracle, L, splits=splits, inverse_factor=12345)   # arbitrary inverse_factor
+
+
+def test_out_of_place_keeps_source(emu, oracle):
+    a = oracle.fill_xorshift(1 << 14, SEED, P0)
+    keep = a.copy()
+    plan = emu.plan(14)
+    out = np.empty_like(a)
+    plan.forward(out.ctypes.data, a.ctypes.data)
+    assert np.array_equal(a, keep)
+
+
+def test_edge_inputs(emu, oracle):
+    """All-zero, all p-1, a delta and a constant vector (values the lazy arithmetic must survive)."""
+    for L, splits in [(12, None), (14, None)]:
+        m = 1 << L
+        plan = emu.plan(L, splits=splits)
+        for a in (np.zeros(m, np.uint64), np.full(m, P0 - 1, np.uint64),
+                  np.eye(1, m, 0, dtype=np.uint64)[0] * np.uint64(P0 - 1), np.full(m, 1, np.uint64)):
+            a = np.ascontiguousarray(a)
+            out = np.empty_like(a)
+            plan.forward(out.ctypes.data, a.ctypes.data)
+            assert np.array_equal(out, oracle.ntt_forward(a, P0, G0))
+            assert (out < np.uint64(P0)).all()
+            back = np.empty_like(a)
+            plan.inverse(back.ctypes.data, out.ctypes.data)
+            assert np.array_equal(back, a)
+
+
+def test_padic64_elementwise(emu, oracle):
+    rng = np.random.default_rng(5)
+    edge = np.array([0, 1, 2, P0 - 1, P0 - 2, 2**63, 2**32, 2**32 - 1, 0x3917FFFFFFF], dtype=np.uint64)
+    a = np.concatenate([np.repeat(edge, edge.size), rng.integers(0, P0, 4000, dtype=np.uint64)])
+    b = np.concatenate([np.tile(edge, edge.size), rng.integers(0, P0, 4000, dtype=np.uint64)])
+    plan = emu.plan(4)
+    bm, back, prod = np.empty_like(b), np.empty_like(b), np.empty_like(a)
+    plan.to_montgomery(bm.ctypes.data, b.ctypes.data, b.size)
+    assert all(int(x) == oracle.to_montgomery(int(y), P0) for x, y in zip(bm[:200], b[:200]))
+    plan.from_montgomery(back.ctypes.data, bm.ctypes.data, b.size)
+    assert np.array_equal(back, b)
+    plan.multiply_normalize(prod.ctypes.data, a.ctypes.data, bm.ctypes.data, a.size)
+    assert np.array_equal(prod, oracle.pointwise_mul(a, b, P0))
+
+
+def test_polynomial_multiply(emu, oracle):
+    """forward, point-wise multiply_normalize against a to_montgomery'd spectrum, inverse
+    (examples/magic-series/gaussian-polynomial.hpp:176-214) == schoolbook cyclic convolution."""
+    L = 8
+    m = 1 << L
+    rng = np.random.default_rng(7)
+    a = np.zeros(m, np.uint64)
+    b = np.zeros(m, np.uint64)
+    a[:m // 2] = rng.integers(0, P0, m // 2, dtype=np.uint64)
+    b[:m // 2] = rng.integers(0, P0, m // 2, dtype=np.uint64)
+    plan = emu.plan(L)
+    fa, fb = np.empty_like(a), np.empty_like(b)
+    plan.forward(fa.ctypes.data, a.ctypes.data)
+    plan.forward(fb.ctypes.data, b.ctypes.data)
+    plan.to_montgomery(fb.ctypes.data, fb.ctypes.data, m)
+    plan.multiply_normalize(fa.ctypes.data, fa.ctypes.data, fb.ctypes.data, m)
+    plan.inverse(fa.ctypes.data, fa.ctypes.data)
+    want = [0] * m
+    ai, bi = [int(v) for v in a[:m // 2]], [int(v) for v in b[:m // 2]]
+    for i, x in enumerate(ai):
+        for j, y in enumerate(bi):
+            want[i + j] = (want[i + j] + x * y) % P0
+    assert [int(v) for v in fa] == want
+
+
+def test_error_paths(emu, pkg):
+    """Same failure classes as the reference: invalid_argument for impossible shapes/roots,
+    logic_error for a direction that was not prepared."""
+    with pytest.raises(pkg.XnttError) as e:
+        emu.plan(40)
+    assert e.value.status == pkg.ERR_INVALID
+    with pytest.raises(pkg.XnttError) as e:
+        emu.plan(10, splits=[4, 4])  # product of radices != m (iterative.hpp:24-27)
+    assert e.value.status == pkg.ERR_INVALID
+    with pytest.raises(pkg.XnttError) as e:
+        emu.plan(10, modulus=0xFFFFFC6E80000001 - 2)  # even / not prime
+    assert e.value.status == pkg.ERR_INVALID
+    with pytest.raises(pkg.XnttError) as e:
+        emu.plan(10, modulus=0x3A00000000000001)  # prime, but other moduli are not built yet
+    assert e.value.status == pkg.ERR_UNSUPPORTED
+    with pytest.raises(pkg.XnttError) as e:
+        emu.plan(10, generator=1)  # not a generator of the order-m subgroup
+    assert e.value.status == pkg.ERR_INVALID
+    plan = emu.plan(6, inverse=False)
+    buf = np.zeros(64, np.uint64)
+    plan.forward(buf.ctypes.data, buf.ctypes.data)
+    with pytest.raises(pkg.XnttError) as e:
+        plan.inverse(buf.ctypes.data, buf.ctypes.data)
+    assert e.value.status == pkg.ERR_STATE
+
+
+def test_sharded_plan_matches_single(emu, oracle):
+    """Distributed six-step with the exchange done by numpy: every rank runs
+    the column half on its column block, tiles are exchanged all-to-all, every rank runs the row
+    half; the concatenated result equals the oracle's transform.  Inverse mirrors it."""
+    for L, splits, G in [(14, [7, 7], 2), (16, [6, 5, 5], 4), (16, [8, 8], 8)]:
+        m = 1 << L
+        n0 = 1 << splits[0]
+        n1 = m // n0
+        a = oracle.fill_xorshift(m, SEED + 3, P0)
+        want = oracle.ntt_forward(a, P0, G0)
+        A = a.reshape(n0, n1)
+        plans = [emu.plan(L, splits=splits, shard_count=G, shard_rank=r) for r in range(G)]
+        cols = []
+        for r in range(G):
+            blk = np.ascontiguousarray(A[:, r * n1 // G:(r + 1) * n1 // G])
+            plans[r].shard_forward_cols(blk.ctypes.data, blk.ctypes.data)
+            cols.append(blk)
+        outs = []
+        for r in range(G):
+            rows = np.ascontiguousarray(
+                np.concatenate([cols[s][r * n0 // G:(r + 1) * n0 // G, :] for s in range(G)], axis=1))
+            plans[r].shard_forward_rows(rows.ctypes.data, rows.ctypes.data)
+            outs.append(rows)
+        got = np.concatenate([o.reshape(-1) for o in outs])
+        assert np.array_equal(got, want), (L, splits, G)
+        # inverse: rows first, exchange back, columns
+        for r in range(G):
+            plans[r].shard_inverse_rows(outs[r].ctypes.data, outs[r].ctypes.data)
+        back = np.empty_like(A)
+        for r in range(G):
+            blk = np.ascontiguousarray(
+                np.concatenate([outs[s][:, r * n1 // G:(r + 1) * n1 // G] for s in range(G)], axis=0))
+            plans[r].shard_inverse_cols(blk.ctypes.data, blk.ctypes.data)
+            back[:, r * n1 // G:(r + 1) * n1 // G] = blk
+        assert np.array_equal(back.reshape(-1), a), (L, splits, G)

@@ -1,0 +1,287 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Parity tests proper: the CUDA path, called through the C ABI (include/xntt.h) with device
+pointers, against the CPU oracle on the same seeded inputs - bit exact.  Shapes follow the
+reference's ntt-tests (tests/ntt-tests/*.hpp), its README example and BASELINE.json's configs; at
+full size, size-independent properties (round trip, linearity, directly evaluated output words)
+complement the word-for-word comparison."""
+import numpy as np
+import pytest
+
+from conftest import G0, P0, SEED
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(a.view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check_against_oracle(lib, oracle, L, splits=None, batch=1, inverse_factor=None, check_batches=None):
+    import torch
+    m = 1 << L
+    a = oracle.fill_xorshift(m * batch, SEED + L, P0)
+    plan = lib.plan(L, splits=splits, batch=batch, inverse_factor=inverse_factor)
+    src = dev(a)
+    dst = torch.full_like(src, 0x5555555555555555)  # bench-ntt.cpp:34 poisons dst
+    plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+    got = host(dst)
+    assert np.array_equal(host(src), a), "out-of-place transform modified its source"
+    for b in (check_batches if check_batches is not None else range(batch)):
+        want = oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), P0, G0)
+        assert np.array_equal(got[b * m:(b + 1) * m], want), (L, plan.splits, b)
+    assert (got < np.uint64(P0)).all(), "non-canonical output word"
+    back = torch.empty_like(src)
+    plan.inverse(back.data_ptr(), dst.data_ptr(), stream())
+    f = m if inverse_factor is None else inverse_factor
+    scale = np.full_like(a, (m * pow(f, -1, P0)) % P0)
+    assert np.array_equal(host(back), oracle.pointwise_mul(a, scale, P0)), (L, plan.splits)
+    # in place
+    buf = src.clone()
+    plan.forward(buf.data_ptr(), buf.data_ptr(), stream())
+    assert np.array_equal(host(buf), got)
+    plan.close()
+    return got
+
+
+@pytest.mark.parametrize("L", range(1, 21))
+def test_forward_inverse_all_sizes(cuda_lib, oracle, L):
+    check_against_oracle(cuda_lib, oracle, L)
+
+
+@pytest.mark.parametrize("L,splits", [
+    (17, [8, 9]),   # README.md:28-68 (BASELINE configs[0])
+    (13, [9, 4]), (15, [9, 6]),  # four-step shapes of tests/ntt-tests
+    (13, [1, 12]), (14, [12, 2]), (10, [5, 5]), (16, [5, 5, 6]), (18, [6, 6, 6]), (20, [10, 10]), (21, [7, 7, 7]),
+])
+def test_explicit_decompositions(cuda_lib, oracle, L, splits):
+    check_against_oracle(cuda_lib, oracle, L, splits=splits)
+
+
+@pytest.mark.parametrize("L,batch", [(3, 1000), (6, 37), (10, 7), (12, 5), (13, 3), (15, 3), (17, 2)])
+def test_batches_and_ragged_tiles(cuda_lib, oracle, L, batch):
+    check_against_oracle(cuda_lib, oracle, L, batch=batch)
+
+
+@pytest.mark.parametrize("L,splits", [(9, None), (12, None), (14, None), (16, [5, 5, 6])])
+def test_inverse_factor(cuda_lib, oracle, L, splits):
+    check_against_oracle(cuda_lib, oracle, L, splits=splits, inverse_factor=1)
+    check_against_oracle(cuda_lib, oracle, L, splits=splits, inverse_factor=0xDEADBEEFCAFE)
+
+
+def test_golden_fingerprints(cuda_lib, oracle, golden):
+    """Fingerprints generated from the reference's NTTReference (tests/golden/make_golden.py)."""
+    import torch
+    for case in golden["spot"]:
+        L = case["log2_m"]
+        a = oracle.fill_xorshift(1 << L, SEED, P0)
+        plan = cuda_lib.plan(L)
+        src = dev(a)
+        out = torch.empty_like(src)
+        for name, fn in (("forward", plan.forward), ("inverse", plan.inverse)):
+            fn(out.data_ptr(), src.data_ptr(), stream())
+            v = host(out)
+            want = case[name]
+            assert f"{int(v[0]):016x}" == want["first"]
+            assert f"{int(v[v.size // 2]):016x}" == want["mid"]
+            assert f"{int(v[-1]):016x}" == want["last"]
+            assert f"{oracle.fnv64(v):016x}" == want["fnv"], (L, name)
+        plan.close()
+
+
+def test_golden_full_vectors(cuda_lib, golden):
+    import torch
+    for case in golden["full"]:
+        if int(case["modulus"], 16) != P0:
+            continue
+        a = np.array([int(v, 16) for v in case["input"]], dtype=np.uint64)
+        plan = cuda_lib.plan(case["log2_m"])
+        src = dev(a)
+        out = torch.empty_like(src)
+        plan.forward(out.data_ptr(), src.data_ptr(), stream())
+        assert [f"{int(v):016x}" for v in host(out)] == case["forward"]
+        plan.inverse(out.data_ptr(), src.data_ptr(), stream())
+        assert [f"{int(v):016x}" for v in host(out)] == case["inverse"]
+        plan.close()
+
+
+def test_edge_inputs(cuda_lib, oracle):
+    import torch
+    for L in (12, 16):
+        m = 1 << L
+        plan = cuda_lib.plan(L)
+        delta = np.zeros(m, np.uint64)
+        delta[1] = P0 - 1
+        for a in (np.zeros(m, np.uint64), np.full(m, P0 - 1, np.uint64), delta, np.full(m, 1, np.uint64)):
+            src = dev(a)
+            out = torch.empty_like(src)
+            plan.forward(out.data_ptr(), src.data_ptr(), stream())
+            assert np.array_equal(host(out), oracle.ntt_forward(a, P0, G0))
+            plan.inverse(out.data_ptr(), out.data_ptr(), stream())
+            assert np.array_equal(host(out), a)
+        plan.close()
+
+
+def test_padic64_elementwise(cuda_lib, oracle):
+    """L0 of SURVEY.md section 4: the device modmul against 128-bit integer arithmetic on random and
+    edge operands (0, 1, p-1, 2^32 boundaries, lazy values >= p)."""
+    import torch
+    rng = np.random.default_rng(5)
+    edge = np.array([0, 1, 2, P0 - 1, P0 - 2, 2**63, 2**32, 2**32 - 1, 0x3917FFFFFFF, 0x80000001, 0xFFFFFC6E],
+                    dtype=np.uint64)
+    a = np.concatenate([np.repeat(edge, edge.size), rng.integers(0, P0, 1 << 16, dtype=np.uint64)])
+    b = np.concatenate([np.tile(edge, edge.size), rng.integers(0, P0, 1 << 16, dtype=np.uint64)])
+    plan = cuda_lib.plan(4)
+    da, db = dev(a), dev(b)
+    bm, back, prod = torch.empty_like(db), torch.empty_like(db), torch.empty_like(da)
+    plan.to_montgomery(bm.data_ptr(), db.data_ptr(), b.size, stream())
+    r = (1 << 64) % P0
+    assert [int(v) for v in host(bm)[:300]] == [int(v) * r % P0 for v in b[:300]]
+    plan.from_montgomery(back.data_ptr(), bm.data_ptr(), b.size, stream())
+    assert np.array_equal(host(back), b)
+    plan.multiply_normalize(prod.data_ptr(), da.data_ptr(), bm.data_ptr(), a.size, stream())
+    assert np.array_equal(host(prod), oracle.pointwise_mul(a, b, P0))
+    # lazy (non-canonical) left operands: a + p still stands for a
+    lazy = a[a < np.uint64(2**64 - P0)] + np.uint64(P0)
+    small = a[a < np.uint64(2**64 - P0)]
+    dl = dev(lazy)
+    out = torch.empty_like(dl)
+    plan.multiply_normalize(out.data_ptr(), dl.data_ptr(), bm[:lazy.size].data_ptr(), lazy.size, stream())
+    assert np.array_equal(host(out), oracle.pointwise_mul(small, b[:lazy.size].copy(), P0))
+    plan.close()
+
+
+def test_polynomial_multiply(cuda_lib, oracle):
+    """BASELINE configs[4]: forward, point-wise multiply_normalize against a to_montgomery'd
+    spectrum, inverse (examples/magic-series/gaussian-polynomial.hpp:176-214)."""
+    import torch
+    L = 15  # the reference's GaussianPolynomialCoefficient test length (test-magic-series.cpp:304)
+    m = 1 << L
+    rng = np.random.default_rng(7)
+    a = np.zeros(m, np.uint64)
+    b = np.zeros(m, np.uint64)
+    a[:m // 2] = rng.integers(0, P0, m // 2, dtype=np.uint64)
+    b[:m // 2] = rng.integers(0, P0, m // 2, dtype=np.uint64)
+    plan = cuda_lib.plan(L)
+    da, db = dev(a), dev(b)
+    plan.forward(da.data_ptr(), da.data_ptr(), stream())
+    plan.forward(db.data_ptr(), db.data_ptr(), stream())
+    plan.to_montgomery(db.data_ptr(), db.data_ptr(), m, stream())
+    plan.multiply_normalize(da.data_ptr(), da.data_ptr(), db.data_ptr(), m, stream())
+    plan.inverse(da.data_ptr(), da.data_ptr(), stream())
+    want = oracle.ntt_inverse(oracle.pointwise_mul(oracle.ntt_forward(a, P0, G0), oracle.ntt_forward(b, P0, G0), P0),
+                              P0, G0)
+    assert np.array_equal(host(da), want)
+    # a few coefficients by schoolbook convolution
+    ai, bi = [int(v) for v in a[:64]], [int(v) for v in b[:64]]
+    for k in (0, 1, 17, 63):
+        assert int(want[k]) == sum(ai[i] * bi[k - i] for i in range(k + 1)) % P0
+    plan.close()
+
+
+def test_host_entry_points(cuda_lib, oracle):
+    a = oracle.fill_xorshift(1 << 16, SEED, P0)
+    plan = cuda_lib.plan(16)
+    out, back = np.empty_like(a), np.empty_like(a)
+    plan.forward_host(out.ctypes.data, a.ctypes.data)
+    assert np.array_equal(out, oracle.ntt_forward(a, P0, G0))
+    plan.inverse_host(back.ctypes.data, out.ctypes.data)
+    assert np.array_equal(back, a)
+    plan.close()
+
+
+def test_full_size_2p24(cuda_lib, oracle):
+    """BASELINE configs[1]: n = 2^24 on one GPU, word for word against the oracle, plus round trip,
+    linearity and directly evaluated output words."""
+    import torch
+    L = 24
+    m = 1 << L
+    a = oracle.fill_xorshift(m, SEED, P0)
+    b = oracle.fill_xorshift(m, SEED ^ 0xABCDEF, P0)
+    plan = cuda_lib.plan(L)
+    da, db = dev(a), dev(b)
+    fa, fb = torch.empty_like(da), torch.empty_like(db)
+    plan.forward(fa.data_ptr(), da.data_ptr(), stream())
+    plan.forward(fb.data_ptr(), db.data_ptr(), stream())
+    ha = host(fa)
+    assert (int(ha[0]), int(ha[1]), int(ha[m // 2])) == (0x94D8DBE8AB43AB69, 0x21E752B9803B0FD6, 0x0D2A95309AC7D97B)
+    assert np.array_equal(ha, oracle.ntt_forward(a, P0, G0))
+    for pos in (0, 1, 12345, m // 2 + 7, m - 1):
+        assert int(ha[pos]) == oracle.dft_point(a, P0, G0, pos)
+    # linearity: F(a + b) == F(a) + F(b)
+    s = (a.astype(object) + b.astype(object)) % P0
+    s = np.array(s, dtype=np.uint64)
+    fs = torch.empty_like(da)
+    plan.forward(fs.data_ptr(), dev(s).data_ptr(), stream())
+    hb = host(fb)
+    sum_f = np.array((ha.astype(object) + hb.astype(object)) % P0, dtype=np.uint64)
+    assert np.array_equal(host(fs), sum_f)
+    back = torch.empty_like(da)
+    plan.inverse(back.data_ptr(), fa.data_ptr(), stream())
+    assert np.array_equal(host(back), a)
+    plan.close()
+
+
+def test_batched_256x2p20(cuda_lib, oracle):
+    """BASELINE configs[2] on one GPU: 256 transforms of 2^20 in one call."""
+    import torch
+    L, batch = 20, 256
+    m = 1 << L
+    plan = cuda_lib.plan(L, batch=batch)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(9)
+    src = torch.randint(0, 2**62, (m * batch,), dtype=torch.int64, device="cuda", generator=gen)
+    dst = torch.empty_like(src)
+    plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+    for b in (0, 131, 255):
+        a = host(src[b * m:(b + 1) * m])
+        assert np.array_equal(host(dst[b * m:(b + 1) * m]), oracle.ntt_forward(a.copy(), P0, G0))
+    plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
+    assert torch.equal(dst, src)
+    plan.close()
+
+
+@pytest.mark.parametrize("L", [26, 28])
+def test_three_pass_sizes(cuda_lib, oracle, L):
+    """Sizes whose shards BASELINE configs[3] hands to one GPU: round trip and direct spot words."""
+    import torch
+    m = 1 << L
+    plan = cuda_lib.plan(L)
+    assert len(plan.splits) == 3
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(L)
+    src = torch.randint(0, 2**62, (m,), dtype=torch.int64, device="cuda", generator=gen)
+    dst = torch.empty_like(src)
+    plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+    if L <= 26:
+        a = host(src)
+        for pos in (0, 3, m // 2 + 1, m - 1):
+            assert int(dst[pos].item()) & (2**64 - 1) == oracle.dft_point(a, P0, G0, pos)
+    plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
+    assert torch.equal(dst, src)
+    plan.close()
+
+
+def test_error_paths(cuda_lib, pkg):
+    with pytest.raises(pkg.XnttError) as e:
+        cuda_lib.plan(10, splits=[4, 4])
+    assert e.value.status == pkg.ERR_INVALID
+    with pytest.raises(pkg.XnttError) as e:
+        cuda_lib.plan(10, modulus=0x3A00000000000001)
+    assert e.value.status == pkg.ERR_UNSUPPORTED
+    plan = cuda_lib.plan(6, forward=False)
+    import torch
+    buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+    with pytest.raises(pkg.XnttError) as e:
+        plan.forward(buf.data_ptr(), buf.data_ptr(), stream())
+    assert e.value.status == pkg.ERR_STATE
+    plan.close()
