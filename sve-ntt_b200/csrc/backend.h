@@ -24,10 +24,13 @@ int pointer_is_device(const void* p, int* is_device);
 const char* last_error();
 
 int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void* stream);
-int launch_gen_table(Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t, void* stream);
-int launch_to_mont(u64* dst, const u64* src, size_t n, u64 r2, void* stream);
-int launch_from_mont(u64* dst, const u64* src, size_t n, void* stream);
-int launch_mulnorm(u64* dst, const u64* a, const u64* b, size_t n, void* stream);
+// the field is chosen by fc.p: kP0 runs the kernels with the modulus baked in, anything else the
+// runtime-modulus kernels (PassParams carries its own copy in prm.field)
+int launch_gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t,
+                     void* stream);
+int launch_to_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, u64 r2, void* stream);
+int launch_from_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, void* stream);
+int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, size_t n, void* stream);
 int microbench(int kind, int iters, double* gops, double* ms);
 
 }  // namespace be

@@ -24,25 +24,26 @@ static int fail(cudaError_t e) {
   } while (0)
 
 template <class F>
-__global__ void gen_table_kernel(Tw* out, u32 count, int kind, int logn, int shift, const __grid_constant__ PowTable t) {
+__global__ void gen_table_kernel(const F f, Tw* out, u32 count, int kind, int logn, int shift,
+                                 const __grid_constant__ PowTable t) {
   const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < count) out[idx] = table_entry<F>(idx, kind, logn, shift, t);
+  if (idx < count) out[idx] = table_entry<F>(f, idx, kind, logn, shift, t);
 }
 template <class F>
-__global__ void to_mont_kernel(u64* dst, const u64* src, size_t n, u64 r2) {
-  const u64 r2p = F::companion(r2);
+__global__ void to_mont_kernel(const F f, u64* dst, const u64* src, size_t n, u64 r2) {
+  const u64 r2p = f.companion(r2);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = ew_to_mont<F>(src[i], r2, r2p);
+    dst[i] = ew_to_mont<F>(f, src[i], r2, r2p);
 }
 template <class F>
-__global__ void from_mont_kernel(u64* dst, const u64* src, size_t n) {
+__global__ void from_mont_kernel(const F f, u64* dst, const u64* src, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = ew_from_mont<F>(src[i]);
+    dst[i] = ew_from_mont<F>(f, src[i]);
 }
 template <class F>
-__global__ void mulnorm_kernel(u64* dst, const u64* a, const u64* b, size_t n) {
+__global__ void mulnorm_kernel(const F f, u64* dst, const u64* a, const u64* b, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = ew_mulnorm<F>(a[i], b[i]);
+    dst[i] = ew_mulnorm<F>(f, a[i], b[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -99,11 +100,12 @@ __global__ void __launch_bounds__(256) microbench_kernel(u64* out, int iters, u3
     u64 x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = ((u64)tid << 32) + i * 0x9e3779b97f4a7c15ull;
-    const u64 w = (((u64)a << 32) | b) % F0::P, wp = F0::companion(w);
+    const F0 f{};
+    const u64 w = (((u64)a << 32) | b) % kP0, wp = f.companion(w);
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int i = 0; i < 8; i += 2) F0::ct_butterfly(x[i], x[i + 1], w, wp);
+      for (int i = 0; i < 8; i += 2) f.ct_butterfly(x[i], x[i + 1], w, wp);
     }
     u64 s = 0;
 #pragma unroll
@@ -205,17 +207,40 @@ const char* last_error() { return g_err.c_str(); }
 int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (col)
-    e = inverse ? launch_inv_col(logn, prm, grid, st) : launch_fwd_col(logn, prm, grid, st);
-  else
-    e = inverse ? launch_inv_row(logn, prm, grid, st) : launch_fwd_row(logn, prm, grid, st);
+  if (prm.field.p == kP0) {
+    if (col)
+      e = inverse ? launch_inv_col(logn, prm, grid, st) : launch_fwd_col(logn, prm, grid, st);
+    else
+      e = inverse ? launch_inv_row(logn, prm, grid, st) : launch_fwd_row(logn, prm, grid, st);
+  } else {
+    if (col)
+      e = inverse ? launch_inv_col_rt(logn, prm, grid, st) : launch_fwd_col_rt(logn, prm, grid, st);
+    else
+      e = inverse ? launch_inv_row_rt(logn, prm, grid, st) : launch_fwd_row_rt(logn, prm, grid, st);
+  }
   if (e != cudaSuccess) return fail(e);
   return 0;
 }
 
-int launch_gen_table(Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t, void* stream) {
+// run `call` with the field object matching fc
+#define XNTT_WITH_FIELD(fc, call)                \
+  do {                                           \
+    if ((fc).p == kP0) {                         \
+      typedef F0 F;                              \
+      const F f = make_field<F>(fc);             \
+      call;                                      \
+    } else {                                     \
+      typedef FieldRT F;                         \
+      const F f = make_field<F>(fc);             \
+      call;                                      \
+    }                                            \
+  } while (0)
+
+int launch_gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t,
+                     void* stream) {
   const u32 threads = 128, blocks = (count + threads - 1) / threads;
-  gen_table_kernel<F0><<<blocks, threads, 0, (cudaStream_t)stream>>>(out, count, kind, logn, shift, t);
+  XNTT_WITH_FIELD(fc, (gen_table_kernel<F><<<blocks, threads, 0, (cudaStream_t)stream>>>(f, out, count, kind, logn,
+                                                                                       shift, t)));
   CU(cudaGetLastError());
   return 0;
 }
@@ -225,18 +250,18 @@ static unsigned ew_grid(size_t n) {
   if (b > 148 * 16) b = 148 * 16;
   return b ? (unsigned)b : 1u;
 }
-int launch_to_mont(u64* dst, const u64* src, size_t n, u64 r2, void* st) {
-  to_mont_kernel<F0><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(dst, src, n, r2);
+int launch_to_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, u64 r2, void* st) {
+  XNTT_WITH_FIELD(fc, (to_mont_kernel<F><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(f, dst, src, n, r2)));
   CU(cudaGetLastError());
   return 0;
 }
-int launch_from_mont(u64* dst, const u64* src, size_t n, void* st) {
-  from_mont_kernel<F0><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(dst, src, n);
+int launch_from_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, void* st) {
+  XNTT_WITH_FIELD(fc, (from_mont_kernel<F><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(f, dst, src, n)));
   CU(cudaGetLastError());
   return 0;
 }
-int launch_mulnorm(u64* dst, const u64* a, const u64* b, size_t n, void* st) {
-  mulnorm_kernel<F0><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(dst, a, b, n);
+int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, size_t n, void* st) {
+  XNTT_WITH_FIELD(fc, (mulnorm_kernel<F><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(f, dst, a, b, n)));
   CU(cudaGetLastError());
   return 0;
 }

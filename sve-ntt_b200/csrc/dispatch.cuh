@@ -1,23 +1,26 @@
 // SPDX-License-Identifier: Apache-2.0
-// Launch-side view of the pass kernels: tile shapes per pass length and the four dispatchers
-// (one translation unit each so the heavy template instantiations compile in parallel).
+// Launch-side view of the pass kernels: the dispatchers (one translation unit per direction / mode
+// / field flavour so the heavy template instantiations compile in parallel).
 #pragma once
 #include "pass_kernel.cuh"
 
 namespace xntt {
 
-typedef Field<kP0> F0;
-
+// static-modulus kernels (p = kP0) and runtime-modulus kernels (any odd prime < 2^64)
 cudaError_t launch_fwd_row(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_row(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 
-template <int LOGN, bool COL, bool INV>
+template <class F, int LOGN, bool COL, bool INV>
 cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
   constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
-  auto kern = pass_kernel<F0, LOGN, LOGW, C, COL, INV, COL>;
+  auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, COL>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
@@ -28,8 +31,8 @@ cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-#define XNTT_CASE(L, COL, INV) \
-  case L:                      \
-    return launch_one<L, COL, INV>(prm, grid, st);
+#define XNTT_CASE(F, L, COL, INV) \
+  case L:                         \
+    return launch_one<F, L, COL, INV>(prm, grid, st);
 
 }  // namespace xntt

@@ -104,32 +104,53 @@ __device__ __forceinline__ void sub_borrow_minus(u64 a, u64 b, u32 sub, u64& d, 
 }
 #endif
 
-// Field with a compile-time modulus.  All the lazy-domain identities below only need P < 2^64 odd;
-// the signed IMAD.WIDE correction additionally needs C_LO < 2^31, which holds for the production
-// prime P = 0xfffffc6e80000001 (C = 0x3917fffffff).
+// ------------------------------------------------------------------------------------------------
+// Constant providers.  StaticModulus bakes the modulus into the instruction stream (immediates);
+// RuntimeModulus carries it in registers / the kernel parameter bank so that one set of kernels
+// serves every odd prime below 2^64 (sventt::Modulus<p, g> is a template, i.e. any p).
 template <u64 P_>
-struct Field {
+struct StaticModulus {
+  static constexpr bool kStatic = true;
   static constexpr u64 P = P_;
-  static constexpr u64 C = 0 - P_;  // 2^64 - P
-  static constexpr u32 P_LO = (u32)P_, P_HI = (u32)(P_ >> 32);
-  static constexpr u32 C_LO = (u32)C, C_HI = (u32)(C >> 32);
-  static constexpr u64 PINV = montgomery_inverse(P_);
-  static constexpr bool kSignedFix = (C_LO < 0x80000000u) && (C >> 63) == 0;
+  __host__ __device__ constexpr u64 p() const { return P_; }
+  __host__ __device__ constexpr u64 c() const { return 0 - P_; }  // 2^64 - P
+  __host__ __device__ constexpr u64 pinv() const { return montgomery_inverse(P_); }
+  // 2^64 mod P (Montgomery form of 1)
+  __host__ __device__ constexpr u64 one() const { return (u64)((((unsigned __int128)1) << 64) % P_); }
+};
 
+struct RuntimeModulus {
+  static constexpr bool kStatic = false;
+  FieldConsts k;
+  __host__ __device__ u64 p() const { return k.p; }
+  __host__ __device__ u64 c() const { return 0 - k.p; }
+  __host__ __device__ u64 pinv() const { return k.pinv; }
+  __host__ __device__ u64 one() const { return k.one; }
+};
+
+// All the lazy-domain identities below only need P < 2^64 odd (P + C = 2^64).
+template <class K>
+struct FieldOps : K {
   // v + delta * C (mod 2^64) for delta in {-1, 0, +1} held as a 32-bit two's complement value.
-  // Maps to one IMAD.WIDE (signed) plus one IMAD.
-  static __device__ __forceinline__ u64 fix(u64 v, u32 delta) {
-    if constexpr (kSignedFix) {
-      u64 t = v + (u64)((long long)(int)delta * (long long)(int)C_LO);
-      u32 tl, th;
-      unpack64(t, tl, th);
-      th += delta * C_HI;
-      return pack64(tl, th);
-    } else {
-      // generic: delta = +1 adds C, delta = -1 adds P (== -C mod 2^64)
-      u64 add = (delta == 1u) ? C : ((delta == 0u) ? 0ull : P);
-      return v + add;
+  __device__ __forceinline__ u64 fix(u64 v, u32 delta) const {
+    const u64 C = this->c();
+    const u32 C_LO = (u32)C, C_HI = (u32)(C >> 32);
+    if constexpr (K::kStatic) {
+      if (C_LO < 0x80000000u) {
+        // one signed IMAD.WIDE plus one IMAD
+        u64 t = v + (u64)((long long)(int)delta * (long long)(int)C_LO);
+        u32 tl, th;
+        unpack64(t, tl, th);
+        th += delta * C_HI;
+        return pack64(tl, th);
+      }
     }
+    // unsigned form: (2^32-1)*C_LO overshoots -C_LO by C_LO*2^32, taken back out of the high word
+    u64 t = v + (u64)delta * (u64)C_LO;
+    u32 tl, th;
+    unpack64(t, tl, th);
+    th += delta * C_HI - (delta >> 31) * C_LO;
+    return pack64(tl, th);
   }
 
   // Montgomery product pieces: returns h1 = hi64(a*w), h2 = hi64(q*P) with q = a*w' mod 2^64;
@@ -140,7 +161,11 @@ struct Field {
   // needed instead of the eight a pair of mul.hi.u64 would issue: the low 64 bits of a*w and q*P
   // are equal by construction, so the carry out of the low half of q*P follows from the low half
   // of a*w:  carry2 = [L.hi < lo32(q0*P1 + q1*P0)]  with  L.hi = bits 32..63 of a*w.
-  static __device__ __forceinline__ void mont_parts(u64 a, u64 w, u64 wp, u64& h1, u64& h2) {
+  __device__ __forceinline__ void mont_parts(u64 a, u64 w, u64 wp, u64& h1, u64& h2) const {
+    const u64 P = this->p();
+    const u32 P_LO = (u32)P, P_HI = (u32)(P >> 32);
+    (void)P_LO;
+    (void)P_HI;
 #if defined(XNTT_HOST_EMU)
     // the same partial-product algebra, word by word, in plain C
     const u64 q = a * wp;
@@ -184,29 +209,31 @@ struct Field {
   }
 
   // Canonical Montgomery product (reference: multiply_normalize).
-  static __device__ __forceinline__ u64 mont(u64 a, u64 w, u64 wp) {
+  __device__ __forceinline__ u64 mont(u64 a, u64 w, u64 wp) const {
     u64 h1, h2, u;
     u32 m;
     mont_parts(a, w, wp, h1, h2);
     sub_borrow_mask(h1, h2, u, m);
     return fix(u, m);  // borrow -> subtract C, i.e. add P
   }
-  static __device__ __forceinline__ u64 mont(u64 a, Tw t) { return mont(a, t.w, t.wp); }
+  __device__ __forceinline__ u64 mont(u64 a, Tw t) const { return mont(a, t.w, t.wp); }
 
   // w' for a Montgomery-form w that was not precomputed (reference: precompute).
-  static __device__ __forceinline__ u64 companion(u64 w) { return w * PINV; }
+  __device__ __forceinline__ u64 companion(u64 w) const { return w * this->pinv(); }
 
   // lazy -> canonical
-  static __device__ __forceinline__ u64 canon(u64 v) {
-    if constexpr ((P >> 63) != 0) {
+  __device__ __forceinline__ u64 canon(u64 v) const {
+    const u64 P = this->p();
+    if ((P >> 63) != 0) {
       // v >= P  <=>  v + C carries; then v - P == v + C (mod 2^64)
       u64 t;
       u32 c;
-      add_carry_plus(v, C, 0u, t, c);
+      add_carry_plus(v, this->c(), 0u, t, c);
       return c ? t : v;
-    } else {
-      return v % P;
     }
+    // small moduli: v may exceed P several times over; v * 1 through the Montgomery reducer
+    const u64 o = this->one();
+    return mont(v, o, companion(o));
   }
 
   // Cooley-Tukey butterfly on lazy values: (x0, x1) <- (x0 + x1*omega, x0 - x1*omega).
@@ -216,7 +243,7 @@ struct Field {
   //   x0 - x1*omega = d + (br - borrow(d)) * 2^64,  d = (x0 - u) mod 2^64
   // and 2^64 == C (mod P).  Range: both true values lie in (-P, 2^64 + P), so the repaired value
   // stays inside [0, 2^64) and the final 64-bit add cannot wrap.
-  static __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, u64 w, u64 wp) {
+  __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, u64 w, u64 wp) const {
     u64 h1, h2, u, s, d;
     u32 m, d0, d1;
     mont_parts(x1, w, wp, h1, h2);
@@ -226,12 +253,12 @@ struct Field {
     x0 = fix(s, d0);
     x1 = fix(d, d1);
   }
-  static __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, Tw t) {
+  __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, Tw t) const {
     ct_butterfly(x0, x1, t.w, t.wp);
   }
 
   // Butterfly with omega = 1: (x0, x1) <- (x0 + x1, x0 - x1).  x0 lazy, x1 MUST be canonical.
-  static __device__ __forceinline__ void ct_butterfly_one(u64& x0, u64& x1) {
+  __device__ __forceinline__ void ct_butterfly_one(u64& x0, u64& x1) const {
     u64 s, d;
     u32 d0, d1;
     add_carry_plus(x0, x1, 0u, s, d0);    // d0 = carry
@@ -240,5 +267,23 @@ struct Field {
     x1 = fix(d, d1);
   }
 };
+
+template <u64 P_>
+using Field = FieldOps<StaticModulus<P_>>;
+typedef FieldOps<RuntimeModulus> FieldRT;
+
+// The production prime of the reference README (README.md:19), C = 0x3917fffffff.
+typedef Field<kP0> F0;
+
+template <class F>
+__host__ __device__ __forceinline__ F make_field(const FieldConsts& k) {
+  if constexpr (F::kStatic) {
+    return F{};
+  } else {
+    F f;
+    f.k = k;
+    return f;
+  }
+}
 
 }  // namespace xntt

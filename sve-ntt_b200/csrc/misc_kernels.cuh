@@ -23,11 +23,11 @@ __device__ __forceinline__ int clz32(u32 v) { return __clz(v); }
 #endif
 
 template <class F>
-__device__ __forceinline__ u64 pow_mont(const PowTable& t, u32 e) {
+__device__ __forceinline__ u64 pow_mont(const F& f, const PowTable& t, u32 e) {
   u64 acc = t.scale;
 #pragma unroll 1
   for (int i = 0; e; ++i, e >>= 1)
-    if (e & 1) acc = F::mont(acc, t.sq[i], F::companion(t.sq[i]));
+    if (e & 1) acc = f.mont(acc, t.sq[i], f.companion(t.sq[i]));
   return acc;
 }
 
@@ -46,21 +46,27 @@ __device__ __forceinline__ u32 table_exponent(u32 idx, int kind, int logn, int s
 }
 
 template <class F>
-__device__ __forceinline__ Tw table_entry(u32 idx, int kind, int logn, int shift, const PowTable& t) {
+__device__ __forceinline__ Tw table_entry(const F& f, u32 idx, int kind, int logn, int shift, const PowTable& t) {
   Tw r;
-  r.w = pow_mont<F>(t, table_exponent(idx, kind, logn, shift));
-  r.wp = F::companion(r.w);
+  r.w = pow_mont<F>(f, t, table_exponent(idx, kind, logn, shift));
+  r.wp = f.companion(r.w);
   return r;
 }
 
 // PAdic64::to_montgomery (p-adic-64.hpp:19-22): a * 2^64 mod P, r2 = 2^128 mod P
 template <class F>
-__device__ __forceinline__ u64 ew_to_mont(u64 a, u64 r2, u64 r2p) { return F::mont(a, r2, r2p); }
+__device__ __forceinline__ u64 ew_to_mont(const F& f, u64 a, u64 r2, u64 r2p) {
+  return f.mont(a, r2, r2p);
+}
 // PAdic64::from_montgomery (p-adic-64.hpp:24-38), canonical
 template <class F>
-__device__ __forceinline__ u64 ew_from_mont(u64 a) { return F::mont(a, 1ull, F::PINV); }
+__device__ __forceinline__ u64 ew_from_mont(const F& f, u64 a) {
+  return f.mont(a, 1ull, f.pinv());
+}
 // PAdic64::multiply_normalize (p-adic-64.hpp:101-115) with on-the-fly precompute
 template <class F>
-__device__ __forceinline__ u64 ew_mulnorm(u64 a, u64 b) { return F::mont(a, b, F::companion(b)); }
+__device__ __forceinline__ u64 ew_mulnorm(const F& f, u64 a, u64 b) {
+  return f.mont(a, b, f.companion(b));
+}
 
 }  // namespace xntt

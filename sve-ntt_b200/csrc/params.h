@@ -24,10 +24,24 @@ constexpr int kMaxTileWLog = 5;
 constexpr int tile_logw(int logn) {
   return logn >= kTileLog ? 0 : (kTileLog - logn < kMaxTileWLog ? kTileLog - logn : kMaxTileWLog);
 }
-constexpr int tile_c(int logn) { return tile_logw(logn) >= 1 ? 2 : 1; }
+// Tuning knobs (compile time): residues per thread-task column group and resident CTAs per SM.
+#ifndef XNTT_FORCE_C1
+#define XNTT_FORCE_C1 0
+#endif
+#ifndef XNTT_MINB
+#define XNTT_MINB 2
+#endif
+constexpr int tile_c(int logn) { return (!XNTT_FORCE_C1 && tile_logw(logn) >= 1) ? 2 : 1; }
 
 // The production prime of the reference README (README.md:19): 2^64 - 1827*2^31 + 1.
 constexpr u64 kP0 = 0xfffffc6e80000001ULL;
+
+// Field constants of a runtime modulus (ignored by the kernels specialised for kP0).
+struct FieldConsts {
+  u64 p;     // modulus
+  u64 pinv;  // p^-1 mod 2^64
+  u64 one;   // 2^64 mod p
+};
 
 struct PassParams {
   const u64* src;
@@ -43,6 +57,7 @@ struct PassParams {
   u32 scale_on;        // inverse row mode: multiply outputs by `scale` (else just canonicalise)
   u32 rows;            // row mode: number of valid rows in the buffer (tiles may be ragged)
   Tw scale;
+  FieldConsts field;
 };
 
 // Input of the on-device table generator: out[idx] = scale * root^e(idx), Montgomery pair.

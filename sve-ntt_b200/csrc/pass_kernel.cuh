@@ -187,17 +187,17 @@ __device__ __forceinline__ Tw ld_tw(const Tw* t) {
 // Six-step twiddle of element (k, global column col): omega_M^(bitrev_LOGN(k) * col), looked up as
 // hi[e >> shift] * lo[e & mask] and applied as two Montgomery products (canonical result).
 template <class F, int LOGN>
-__device__ __forceinline__ u64 apply_twist(const PassParams& prm, u64 v, int k, u32 col) {
+__device__ __forceinline__ u64 apply_twist(const F& f, const PassParams& prm, u64 v, int k, u32 col) {
   const u32 e = (__brev((u32)k) >> (32 - LOGN)) * col;
   const Tw lo = ld_tw(prm.twist_lo + (e & ((1u << prm.twist_shift) - 1u)));
   const Tw hi = ld_tw(prm.twist_hi + (e >> prm.twist_shift));
-  return F::mont(F::mont(v, hi), lo);
+  return f.mont(f.mont(v, hi), lo);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Forward radix-R register network (Cooley-Tukey, block-indexed twiddles).
 template <class F, int LOGR, int C, bool FIRST>
-__device__ __forceinline__ void fwd_network(u64 (&x)[1 << LOGR][C], const Tw* __restrict__ G, int B) {
+__device__ __forceinline__ void fwd_network(const F& f, u64 (&x)[1 << LOGR][C], const Tw* __restrict__ G, int B) {
   constexpr int R = 1 << LOGR;
 #pragma unroll
   for (int lam = 0; lam < LOGR; ++lam) {
@@ -210,15 +210,15 @@ __device__ __forceinline__ void fwd_network(u64 (&x)[1 << LOGR][C], const Tw* __
         for (int r0 = 0; r0 < h; ++r0)
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            if (lam > 0) x[r0 + h][c] = F::canon(x[r0 + h][c]);
-            F::ct_butterfly_one(x[r0][c], x[r0 + h][c]);
+            if (lam > 0) x[r0 + h][c] = f.canon(x[r0 + h][c]);
+            f.ct_butterfly_one(x[r0][c], x[r0 + h][c]);
           }
       } else {
         const Tw t = ld_tw(G + ((B << lam) + g));
 #pragma unroll
         for (int r0 = 0; r0 < h; ++r0)
 #pragma unroll
-          for (int c = 0; c < C; ++c) F::ct_butterfly(x[g * 2 * h + r0][c], x[g * 2 * h + r0 + h][c], t);
+          for (int c = 0; c < C; ++c) f.ct_butterfly(x[g * 2 * h + r0][c], x[g * 2 * h + r0 + h][c], t);
       }
     }
   }
@@ -227,7 +227,8 @@ __device__ __forceinline__ void fwd_network(u64 (&x)[1 << LOGR][C], const Tw* __
 // Inverse radix-R register network (decimation in time, position-indexed twiddles).
 // Level lam pairs (r, r + 2^lam); element stride is S, task offset inside its block is i.
 template <class F, int LOGR, int C, bool FIRST>
-__device__ __forceinline__ void inv_network(u64 (&x)[1 << LOGR][C], const Tw* __restrict__ I, int logs, int i) {
+__device__ __forceinline__ void inv_network(const F& f, u64 (&x)[1 << LOGR][C], const Tw* __restrict__ I, int logs,
+                                            int i) {
   constexpr int R = 1 << LOGR;
 #pragma unroll
   for (int lam = 0; lam < LOGR; ++lam) {
@@ -240,15 +241,15 @@ __device__ __forceinline__ void inv_network(u64 (&x)[1 << LOGR][C], const Tw* __
         for (int r = j; r < R; r += 2 * h)
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            if (lam > 0) x[r + h][c] = F::canon(x[r + h][c]);
-            F::ct_butterfly_one(x[r][c], x[r + h][c]);
+            if (lam > 0) x[r + h][c] = f.canon(x[r + h][c]);
+            f.ct_butterfly_one(x[r][c], x[r + h][c]);
           }
       } else {
         const Tw t = ld_tw(I + ((h << logs) + i + (j << logs)));
 #pragma unroll
         for (int r = j; r < R; r += 2 * h)
 #pragma unroll
-          for (int c = 0; c < C; ++c) F::ct_butterfly(x[r][c], x[r + h][c], t);
+          for (int c = 0; c < C; ++c) f.ct_butterfly(x[r][c], x[r + h][c], t);
       }
     }
   }
@@ -258,6 +259,7 @@ __device__ __forceinline__ void inv_network(u64 (&x)[1 << LOGR][C], const Tw* __
 template <class F, class Cfg, bool TWIST, int J>
 __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
                                           const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
+  const F f = make_field<F>(prm.field);
   constexpr int NS = Cfg::NS;
   constexpr int LOGR = (J == 0) ? Cfg::LOGR1 : 3;
   constexpr int R = 1 << LOGR;
@@ -281,16 +283,16 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
       gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
     else
       smem_load<Cfg, R>(sm, k0, LOGS, p, x);
-    fwd_network<F, LOGR, Cfg::C, J == 0>(x, prm.tw, B);
+    fwd_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, B);
     if constexpr (J == NS - 1) {
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < Cfg::C; ++c) {
           if constexpr (TWIST)
-            x[r][c] = apply_twist<F, Cfg::LOGN>(prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
+            x[r][c] = apply_twist<F, Cfg::LOGN>(f, prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
           else
-            x[r][c] = F::canon(x[r][c]);
+            x[r][c] = f.canon(x[r][c]);
         }
       gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
     } else {
@@ -303,6 +305,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
 template <class F, class Cfg, bool TWIST, int J>
 __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
                                           const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
+  const F f = make_field<F>(prm.field);
   constexpr int NS = Cfg::NS;
   // inverse stage J mirrors forward stage NS-1-J
   constexpr int LOGR = (J == NS - 1) ? Cfg::LOGR1 : 3;
@@ -330,23 +333,23 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int c = 0; c < Cfg::C; ++c)
-            x[r][c] = apply_twist<F, Cfg::LOGN>(prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
+            x[r][c] = apply_twist<F, Cfg::LOGN>(f, prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
       }
     } else {
       smem_load<Cfg, R>(sm, k0, LOGS, p, x);
     }
-    inv_network<F, LOGR, Cfg::C, J == 0>(x, prm.tw, LOGS, i);
+    inv_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, LOGS, i);
     if constexpr (J == NS - 1) {
       if (prm.scale_on) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int c = 0; c < Cfg::C; ++c) x[r][c] = F::mont(x[r][c], prm.scale);
+          for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], prm.scale);
       } else {
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int c = 0; c < Cfg::C; ++c) x[r][c] = F::canon(x[r][c]);
+          for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.canon(x[r][c]);
       }
       gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
     } else {
@@ -368,7 +371,7 @@ __device__ __forceinline__ void run_stages(const PassParams& prm, typename Slot<
 
 #if !defined(XNTT_HOST_EMU)
 template <class F, int LOGN, int LOGW, int C, bool COL, bool INVERSE, bool TWIST>
-__global__ void __launch_bounds__(kThreads, 2) pass_kernel(const __grid_constant__ PassParams prm) {
+__global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_constant__ PassParams prm) {
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto* sm = reinterpret_cast<typename Slot<C>::type*>(smem_raw);

@@ -53,6 +53,7 @@ struct xntt_plan {
   bool scale_on = false;
   u64 r2 = 0;  // 2^128 mod p
   u32 shard_count = 1, shard_rank = 0;
+  FieldConsts field{};
   mutable void* staging = nullptr;  // device buffer behind the *_host entry points (lazy)
 };
 
@@ -111,7 +112,8 @@ int choose_splits(int L, std::vector<int>& out) {
   return XNTT_OK;
 }
 
-int gen_table(Tw* out, u32 count, int kind, int logn, int shift, u64 root, u64 scale_plain, u64 p) {
+int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, u64 root, u64 scale_plain) {
+  const u64 p = fc.p;
   PowTable t;
   u64 r = root;
   for (int i = 0; i < 32; ++i) {
@@ -119,7 +121,7 @@ int gen_table(Tw* out, u32 count, int kind, int logn, int shift, u64 root, u64 s
     r = h_mul(r, r, p);
   }
   t.scale = h_to_mont(scale_plain % p, p);
-  BE(be::launch_gen_table(out, count, kind, logn, shift, t, nullptr));
+  BE(be::launch_gen_table(fc, out, count, kind, logn, shift, t, nullptr));
   return XNTT_OK;
 }
 
@@ -133,6 +135,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
   prm.dst = dst;
   prm.tw = inverse ? ps.inv_tw : ps.fwd_tw;
   prm.scale = pl->scale;
+  prm.field = pl->field;
   const int logw = tile_logw(ps.logn);
   unsigned grid;
   if (ps.col) {
@@ -213,10 +216,7 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   if (d->log2_m < 1 || d->log2_m > 31) return XNTT_ERR_INVALID;
   const u64 p = d->modulus, gen = d->generator;
   if ((p & 1) == 0 || p < 3 || gen == 0) return XNTT_ERR_INVALID;
-  if (p != kP0) {
-    // other moduli of Modulus<p, g> are SURVEY section 8(f) "next" work
-    return h_is_prime(p) ? XNTT_ERR_UNSUPPORTED : XNTT_ERR_INVALID;
-  }
+  if (!h_is_prime(p)) return XNTT_ERR_INVALID;  // Modulus<> assumes a prime (modulus.hpp:13)
   const u64 m = 1ull << d->log2_m;
   if ((p - 1) % m != 0) return XNTT_ERR_INVALID;  // Modulus::get_root_forward: invalid_argument
   const u64 root_m = h_pow(gen % p, (p - 1) / m, p);
@@ -278,6 +278,9 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   pl->scale.w = h_to_mont(finv, p);
   pl->scale.wp = pl->scale.w * h_montgomery_inverse(p);
   pl->r2 = h_to_mont(h_to_mont(1, p), p);
+  pl->field.p = p;
+  pl->field.pinv = h_montgomery_inverse(p);
+  pl->field.one = h_to_mont(1, p);
 
   int dev = d->device;
   if (dev < 0) {
@@ -346,8 +349,8 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
     const u64 root_n = h_pow(gen % p, (p - 1) / n, p);
     ps.fwd_tw = base + off_fwd[i];
     ps.inv_tw = base + off_inv[i];
-    rc = gen_table(base + off_fwd[i], (u32)(n / 2 ? n / 2 : 1), kFwdG, ps.logn, 0, root_n, 1, p);
-    if (rc == XNTT_OK) rc = gen_table(base + off_inv[i], (u32)n, kInvI, ps.logn, 0, h_inv(root_n, p), 1, p);
+    rc = gen_table(pl->field, base + off_fwd[i], (u32)(n / 2 ? n / 2 : 1), kFwdG, ps.logn, 0, root_n, 1);
+    if (rc == XNTT_OK) rc = gen_table(pl->field, base + off_inv[i], (u32)n, kInvI, ps.logn, 0, h_inv(root_n, p), 1);
     if (ps.col && rc == XNTT_OK) {
       const int lm = ps.logn + ps.log_inner;
       const u64 root_big = h_pow(gen % p, (p - 1) >> lm, p);
@@ -357,12 +360,12 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
       ps.fwd_hi = base + off_fhi[i];
       ps.inv_lo = base + off_ilo[i];
       ps.inv_hi = base + off_ihi[i];
-      rc = gen_table(base + off_flo[i], nlo, kPowers, 0, 0, root_big, 1, p);
-      if (rc == XNTT_OK) rc = gen_table(base + off_fhi[i], nhi, kPowers, 0, ps.twist_shift, root_big, 1, p);
-      if (rc == XNTT_OK) rc = gen_table(base + off_ilo[i], nlo, kPowers, 0, 0, root_big_inv, 1, p);
+      rc = gen_table(pl->field, base + off_flo[i], nlo, kPowers, 0, 0, root_big, 1);
+      if (rc == XNTT_OK) rc = gen_table(pl->field, base + off_fhi[i], nhi, kPowers, 0, ps.twist_shift, root_big, 1);
+      if (rc == XNTT_OK) rc = gen_table(pl->field, base + off_ilo[i], nlo, kPowers, 0, 0, root_big_inv, 1);
       // the outermost column pass runs last in the inverse: fold 1/inverse_factor into its table
       if (rc == XNTT_OK)
-        rc = gen_table(base + off_ihi[i], nhi, kPowers, 0, ps.twist_shift, root_big_inv, i == 0 ? finv : 1, p);
+        rc = gen_table(pl->field, base + off_ihi[i], nhi, kPowers, 0, ps.twist_shift, root_big_inv, i == 0 ? finv : 1);
     }
   }
   if (rc == XNTT_OK) {
@@ -444,14 +447,14 @@ int xntt_to_montgomery(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, 
   if (!pl || !dst || !src) return XNTT_ERR_INVALID;
   if (n == 0) return XNTT_OK;
   DeviceGuard g(pl->device);
-  BE(be::launch_to_mont((u64*)dst, (const u64*)src, n, pl->r2, st));
+  BE(be::launch_to_mont(pl->field, (u64*)dst, (const u64*)src, n, pl->r2, st));
   return XNTT_OK;
 }
 int xntt_from_montgomery(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, size_t n, void* st) {
   if (!pl || !dst || !src) return XNTT_ERR_INVALID;
   if (n == 0) return XNTT_OK;
   DeviceGuard g(pl->device);
-  BE(be::launch_from_mont((u64*)dst, (const u64*)src, n, st));
+  BE(be::launch_from_mont(pl->field, (u64*)dst, (const u64*)src, n, st));
   return XNTT_OK;
 }
 int xntt_multiply_normalize(const xntt_plan* pl, uint64_t* dst, const uint64_t* a, const uint64_t* b, size_t n,
@@ -459,7 +462,7 @@ int xntt_multiply_normalize(const xntt_plan* pl, uint64_t* dst, const uint64_t* 
   if (!pl || !dst || !a || !b) return XNTT_ERR_INVALID;
   if (n == 0) return XNTT_OK;
   DeviceGuard g(pl->device);
-  BE(be::launch_mulnorm((u64*)dst, (const u64*)a, (const u64*)b, n, st));
+  BE(be::launch_mulnorm(pl->field, (u64*)dst, (const u64*)a, (const u64*)b, n, st));
   return XNTT_OK;
 }
 

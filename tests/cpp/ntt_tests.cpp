@@ -4,8 +4,8 @@
 // for every kernel composition of tests/ntt-tests/*.hpp (and the README example) build
 // sventt::NTT<kernel_type>, transform an iota input out of place with dst poisoned, and require
 // dst[i] % N == reference[i] for all i, forward and inverse.  The compositions are spelled exactly
-// as in the reference, with the production modulus of README.md:19 in place of the 62-bit test
-// modulus (other moduli are SURVEY section 8(f) work).  The expected vectors come from the CPU
+// as in the reference, including its 62-bit test modulus 0x3a00000000000001 (README example and the
+// 2^24 shape: the production modulus of README.md:19).  The expected vectors come from the CPU
 // oracle (oracle/ntt_oracle.c) - this file is test code, the only place allowed to link it.
 #include <sventt/sventt.hpp>
 
@@ -28,9 +28,14 @@ void oracle_ntt_inverse(std::uint64_t* dst, const std::uint64_t* src, std::uint6
 
 using namespace sventt;
 
-using modulus_type = Modulus<UINT64_C(0xfffffc6e80000001), UINT64_C(3)>;
-using modmul_type = PAdic64SVE<modulus_type>;
 constexpr std::uint64_t one = 1;
+namespace prod {
+using modulus_type = Modulus<UINT64_C(0xfffffc6e80000001), UINT64_C(3)>;  // README.md:19
+using modmul_type = PAdic64SVE<modulus_type>;
+}  // namespace prod
+// tests/ntt-tests/*.hpp
+using modulus_type = Modulus<UINT64_C(0x3a00000000000001), UINT64_C(3)>;
+using modmul_type = PAdic64SVE<modulus_type>;
 
 // ---- tests/ntt-tests/iterative-sve-radix2-two10.hpp
 namespace it_r2 {
@@ -108,6 +113,8 @@ using kernel_type = RecursiveNTT<modulus_type, m, GenericScalarLayer<modmul_type
 }  // namespace rec_four13
 // ---- README.md:14-71: blocked six-step, 2^17 = 2^8 x 2^9, unscaled inverse
 namespace readme {
+using modulus_type = prod::modulus_type;
+using modmul_type = prod::modmul_type;
 using transposition_type = TransposeParallelSVEInRegisterExplicitBlockingRowFirst<32, 128, 128 + 32, 3>;
 constexpr std::uint64_t n = one << 17, n0 = one << 8, n1 = one << 9;
 using ntt0_type = IterativeNTT<modulus_type, n0, RadixEightSVELayer<modmul_type, n0, n0>,
@@ -122,6 +129,8 @@ using kernel_type =
 }  // namespace readme
 // ---- BASELINE configs[1] spelled with the reference's classes: 2^24 = 2^12 x 2^12 blocked six-step
 namespace big24 {
+using modulus_type = prod::modulus_type;
+using modmul_type = prod::modmul_type;
 constexpr std::uint64_t n = one << 24, n0 = one << 12, n1 = one << 12;
 template <std::uint64_t len, std::uint64_t f>
 using inner = IterativeNTT<modulus_type, len, RadixEightSVELayer<modmul_type, len, len>,
@@ -203,6 +212,7 @@ int main(int argc, char** argv) {
     both<readme::kernel_type>("README blocked six-step 2^8 x 2^9");
     if (big) both<big24::kernel_type>("blocked six-step 2^12 x 2^12");
     // Modulus / PAdic64 scalar identities used by the examples
+    using modulus_type = prod::modulus_type;
     using P = PAdic64<modulus_type>;
     static_assert(modulus_type::get_montgomery_inverse() == UINT64_C(0x4000039180000001));
     static_assert(P::to_montgomery(1) == UINT64_C(0x3917fffffff));

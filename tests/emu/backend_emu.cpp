@@ -40,29 +40,28 @@ static inline unsigned __brev(unsigned v) {
 #include "../../sve-ntt_b200/csrc/pass_kernel.cuh"
 
 namespace xntt {
-typedef Field<kP0> F0;
 
-template <class Cfg, bool INV, bool TWIST, int J>
+template <class F, class Cfg, bool INV, bool TWIST, int J>
 static void emu_stage_all_threads(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc,
                                   u64* gdst, u32 col0, u32 row0) {
   for (unsigned t = 0; t < (unsigned)kThreads; ++t) {
     threadIdx.x = t;
     if constexpr (INV)
-      inv_stage<F0, Cfg, TWIST, J>(prm, sm, gsrc, gdst, col0, row0);
+      inv_stage<F, Cfg, TWIST, J>(prm, sm, gsrc, gdst, col0, row0);
     else
-      fwd_stage<F0, Cfg, TWIST, J>(prm, sm, gsrc, gdst, col0, row0);
+      fwd_stage<F, Cfg, TWIST, J>(prm, sm, gsrc, gdst, col0, row0);
   }
 }
 
-template <class Cfg, bool INV, bool TWIST, int... Js>
+template <class F, class Cfg, bool INV, bool TWIST, int... Js>
 static void emu_stages(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc, u64* gdst,
                        u32 col0, u32 row0, std::integer_sequence<int, Js...>) {
   // a stage ends with a block-wide barrier: run every emulated thread through stage J, then J + 1
-  (emu_stage_all_threads<Cfg, INV, TWIST, Js>(prm, sm, gsrc, gdst, col0, row0), ...);
+  (emu_stage_all_threads<F, Cfg, INV, TWIST, Js>(prm, sm, gsrc, gdst, col0, row0), ...);
 }
 
-template <int LOGN, bool COL, bool INV>
-static int emu_launch(const PassParams& prm, unsigned grid) {
+template <class F, int LOGN, bool COL, bool INV>
+static int emu_launch2(const PassParams& prm, unsigned grid) {
   constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
   std::vector<typename Slot<C>::type> sm((size_t)Cfg::N * Cfg::NP + 1);
@@ -80,10 +79,17 @@ static int emu_launch(const PassParams& prm, unsigned grid) {
     }
     // poison shared memory so that a missing write shows up
     memset(sm.data(), 0xcd, sm.size() * sizeof(sm[0]));
-    emu_stages<Cfg, INV, COL>(prm, sm.data(), prm.src + base, prm.dst + base, col0, row0,
+    emu_stages<F, Cfg, INV, COL>(prm, sm.data(), prm.src + base, prm.dst + base, col0, row0,
                               std::make_integer_sequence<int, Cfg::NS>{});
   }
   return 0;
+}
+
+template <int LOGN, bool COL, bool INV>
+static int emu_launch(const PassParams& prm, unsigned grid) {
+  // same choice as backend_cuda.cu: baked-in modulus for kP0, runtime modulus otherwise
+  if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV>(prm, grid);
+  return emu_launch2<FieldRT, LOGN, COL, INV>(prm, grid);
 }
 
 #define EMU_CASE(L)                                                       \
@@ -150,21 +156,37 @@ int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigne
   return 1;
 }
 
-int launch_gen_table(Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t, void*) {
-  for (u32 i = 0; i < count; ++i) out[i] = table_entry<F0>(i, kind, logn, shift, t);
+#define EMU_WITH_FIELD(fc, call)     \
+  do {                               \
+    if ((fc).p == kP0) {             \
+      typedef F0 F;                  \
+      const F f = make_field<F>(fc); \
+      call;                          \
+    } else {                         \
+      typedef FieldRT F;             \
+      const F f = make_field<F>(fc); \
+      call;                          \
+    }                                \
+  } while (0)
+
+int launch_gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t,
+                     void*) {
+  EMU_WITH_FIELD(fc, for (u32 i = 0; i < count; ++i) out[i] = table_entry<F>(f, i, kind, logn, shift, t));
   return 0;
 }
-int launch_to_mont(u64* dst, const u64* src, size_t n, u64 r2, void*) {
-  const u64 r2p = F0::companion(r2);
-  for (size_t i = 0; i < n; ++i) dst[i] = ew_to_mont<F0>(src[i], r2, r2p);
+int launch_to_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, u64 r2, void*) {
+  EMU_WITH_FIELD(fc, {
+    const u64 r2p = f.companion(r2);
+    for (size_t i = 0; i < n; ++i) dst[i] = ew_to_mont<F>(f, src[i], r2, r2p);
+  });
   return 0;
 }
-int launch_from_mont(u64* dst, const u64* src, size_t n, void*) {
-  for (size_t i = 0; i < n; ++i) dst[i] = ew_from_mont<F0>(src[i]);
+int launch_from_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, void*) {
+  EMU_WITH_FIELD(fc, for (size_t i = 0; i < n; ++i) dst[i] = ew_from_mont<F>(f, src[i]));
   return 0;
 }
-int launch_mulnorm(u64* dst, const u64* a, const u64* b, size_t n, void*) {
-  for (size_t i = 0; i < n; ++i) dst[i] = ew_mulnorm<F0>(a[i], b[i]);
+int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, size_t n, void*) {
+  EMU_WITH_FIELD(fc, for (size_t i = 0; i < n; ++i) dst[i] = ew_mulnorm<F>(f, a[i], b[i]));
   return 0;
 }
 int microbench(int, int, double*, double*) {

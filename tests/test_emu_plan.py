@@ -141,8 +141,8 @@ def test_error_paths(emu, pkg):
         emu.plan(10, modulus=0xFFFFFC6E80000001 - 2)  # even / not prime
     assert e.value.status == pkg.ERR_INVALID
     with pytest.raises(pkg.XnttError) as e:
-        emu.plan(10, modulus=0x3A00000000000001)  # prime, but other moduli are not built yet
-    assert e.value.status == pkg.ERR_UNSUPPORTED
+        emu.plan(20, modulus=0x10001)  # 2^20 does not divide p - 1: the field has no such root
+    assert e.value.status == pkg.ERR_INVALID
     with pytest.raises(pkg.XnttError) as e:
         emu.plan(10, generator=1)  # not a generator of the order-m subgroup
     assert e.value.status == pkg.ERR_INVALID
@@ -189,3 +189,52 @@ def test_sharded_plan_matches_single(emu, oracle):
             plans[r].shard_inverse_cols(blk.ctypes.data, blk.ctypes.data)
             back[:, r * n1 // G:(r + 1) * n1 // G] = blk
         assert np.array_equal(back.reshape(-1), a), (L, splits, G)
+
+
+# moduli of the reference's own tests: ntt-tests (62 bit), test-ntt-reference.cpp:17-23 and
+# examples/magic-series/test-magic-series.cpp:22-39 (64 .. 60 bit, Goldilocks, the Fermat prime)
+OTHER_MODULI = [
+    (0x3A00000000000001, 3), (0xFFFFFFFF00000001, 7), (0xFFFFFFFF00000001, 0xF44872F5EC1C4CC0),
+    (0xA3B25F400C7A8001, 5), (0x41D33D0D1FBF8001, 6), (0x3164C5D59B090001, 13), (0x1E4A0E19E4548001, 3),
+    (0x08AA90297F870001, 3), (0x0000000000010001, 3), (0x0C40000000000001, 5), (0x0C60000000000001, 7),
+    (0x0003F00000000001, 11), (0x0002580000000001, 11),
+]
+
+
+@pytest.mark.parametrize("N,g", OTHER_MODULI)
+def test_other_moduli(emu, oracle, N, g):
+    """Modulus<p, g> is a template: every prime the reference's tests use runs through the
+    runtime-modulus kernels."""
+    for L, splits, batch in [(1, None, 1), (3, None, 5), (7, None, 1), (10, None, 1), (12, None, 2), (13, None, 1),
+                             (15, None, 1), (13, [9, 4], 1), (16, [5, 5, 6], 1)]:
+        if (N - 1) % (1 << L):
+            continue
+        m = 1 << L
+        a = oracle.fill_xorshift(m * batch, SEED + L, N)
+        plan = emu.plan(L, modulus=N, generator=g, splits=splits, batch=batch)
+        out = np.empty_like(a)
+        plan.forward(out.ctypes.data, a.ctypes.data)
+        for b in range(batch):
+            assert np.array_equal(out[b * m:(b + 1) * m], oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), N, g))
+        assert (out < np.uint64(N)).all()
+        back = np.empty_like(a)
+        plan.inverse(back.ctypes.data, out.ctypes.data)
+        assert np.array_equal(back, a)
+        # PAdic64 helpers in this field
+        bm = np.empty_like(a)
+        plan.to_montgomery(bm.ctypes.data, a.ctypes.data, a.size)
+        prod = np.empty_like(a)
+        plan.multiply_normalize(prod.ctypes.data, out.ctypes.data, bm.ctypes.data, a.size)
+        assert np.array_equal(prod, oracle.pointwise_mul(out, a, N))
+
+
+def test_golden_full_vectors_all_moduli(emu, golden):
+    for case in golden["full"]:
+        N, g = int(case["modulus"], 16), case["g"]
+        a = np.array([int(v, 16) for v in case["input"]], dtype=np.uint64)
+        plan = emu.plan(case["log2_m"], modulus=N, generator=g)
+        out = np.empty_like(a)
+        plan.forward(out.ctypes.data, a.ctypes.data)
+        assert [f"{int(v):016x}" for v in out] == case["forward"]
+        plan.inverse(out.ctypes.data, a.ctypes.data)
+        assert [f"{int(v):016x}" for v in out] == case["inverse"]

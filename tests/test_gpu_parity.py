@@ -99,12 +99,12 @@ def test_golden_fingerprints(cuda_lib, oracle, golden):
 
 
 def test_golden_full_vectors(cuda_lib, golden):
+    """All seven moduli of the golden file (test-ntt-reference.cpp's five, the ntt-tests prime, p0)."""
     import torch
     for case in golden["full"]:
-        if int(case["modulus"], 16) != P0:
-            continue
+        N, g = int(case["modulus"], 16), case["g"]
         a = np.array([int(v, 16) for v in case["input"]], dtype=np.uint64)
-        plan = cuda_lib.plan(case["log2_m"])
+        plan = cuda_lib.plan(case["log2_m"], modulus=N, generator=g)
         src = dev(a)
         out = torch.empty_like(src)
         plan.forward(out.data_ptr(), src.data_ptr(), stream())
@@ -276,8 +276,8 @@ def test_error_paths(cuda_lib, pkg):
         cuda_lib.plan(10, splits=[4, 4])
     assert e.value.status == pkg.ERR_INVALID
     with pytest.raises(pkg.XnttError) as e:
-        cuda_lib.plan(10, modulus=0x3A00000000000001)
-    assert e.value.status == pkg.ERR_UNSUPPORTED
+        cuda_lib.plan(20, modulus=0x10001)
+    assert e.value.status == pkg.ERR_INVALID
     plan = cuda_lib.plan(6, forward=False)
     import torch
     buf = torch.zeros(64, dtype=torch.int64, device="cuda")
@@ -285,3 +285,38 @@ def test_error_paths(cuda_lib, pkg):
         plan.forward(buf.data_ptr(), buf.data_ptr(), stream())
     assert e.value.status == pkg.ERR_STATE
     plan.close()
+
+
+OTHER_MODULI = [
+    (0x3A00000000000001, 3), (0xFFFFFFFF00000001, 7), (0xFFFFFFFF00000001, 0xF44872F5EC1C4CC0),
+    (0xA3B25F400C7A8001, 5), (0x41D33D0D1FBF8001, 6), (0x3164C5D59B090001, 13), (0x1E4A0E19E4548001, 3),
+    (0x08AA90297F870001, 3), (0x0000000000010001, 3), (0x0C40000000000001, 5), (0x0002580000000001, 11),
+]
+
+
+@pytest.mark.parametrize("N,g", OTHER_MODULI)
+def test_other_moduli(cuda_lib, oracle, N, g):
+    """The moduli of tests/ntt-tests, tests/test-ntt-reference.cpp:17-23 and
+    examples/magic-series/test-magic-series.cpp:22-39 through the runtime-modulus kernels."""
+    import torch
+    for L, splits, batch in [(1, None, 1), (3, None, 5), (7, None, 1), (10, None, 1), (12, None, 2), (13, None, 1),
+                             (15, None, 1), (13, [9, 4], 1), (16, [5, 5, 6], 1), (20, None, 1)]:
+        if (N - 1) % (1 << L):
+            continue
+        m = 1 << L
+        a = oracle.fill_xorshift(m * batch, SEED + L, N)
+        plan = cuda_lib.plan(L, modulus=N, generator=g, splits=splits, batch=batch)
+        src = dev(a)
+        dst = torch.empty_like(src)
+        plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+        got = host(dst)
+        for b in range(batch):
+            assert np.array_equal(got[b * m:(b + 1) * m], oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), N, g)), (L, b)
+        assert (got < np.uint64(N)).all()
+        plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
+        assert np.array_equal(host(dst), a)
+        bm, prod = torch.empty_like(src), torch.empty_like(src)
+        plan.to_montgomery(bm.data_ptr(), src.data_ptr(), a.size, stream())
+        plan.multiply_normalize(prod.data_ptr(), dev(got).data_ptr(), bm.data_ptr(), a.size, stream())
+        assert np.array_equal(host(prod), oracle.pointwise_mul(got, a, N))
+        plan.close()
