@@ -34,6 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "sve-ntt_b200"))
 
 P0, G0 = 0xFFFFFC6E80000001, 3
 SEED = 0x9E3779B97F4A7C15

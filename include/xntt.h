@@ -84,6 +84,14 @@ int xntt_forward(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void
 /* sventt::NTT<kernel>::compute_inverse(dst, src) / compute_inverse(dst)  (wrapper.hpp:67-82) */
 int xntt_inverse(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
 
+/* Forward transform with the point-wise product of a polynomial multiply fused into its last pass:
+ * dst = multiply_normalize(forward(src), b_mont) word by word, b_mont being a to_montgomery'd
+ * spectrum in the same bit-reversed order (examples/magic-series/gaussian-polynomial.hpp:196-212:
+ * compute_forward followed by the multiply_normalize loop).  xntt_inverse of dst then yields the
+ * cyclic product. */
+int xntt_forward_multiply(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, const uint64_t* b_mont,
+                          void* stream);
+
 /* One pass of a plan on its own (profiling / per-kernel timing): pass index in forward order,
  * inverse != 0 runs the inverse kernel of that pass.  In place or src -> dst like the full calls. */
 int xntt_run_pass(const xntt_plan* plan, uint32_t pass, int inverse, uint64_t* dst, const uint64_t* src,

@@ -55,6 +55,7 @@ SYMBOLS = {
     "xntt_plan_splits": (C.c_uint32, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
     "xntt_forward": (C.c_int, [_P, _U64P, _U64P, _P]),
     "xntt_inverse": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_forward_multiply": (C.c_int, [_P, _U64P, _U64P, _U64P, _P]),
     "xntt_run_pass": (C.c_int, [_P, C.c_uint32, C.c_int, _U64P, _U64P, _P]),
     "xntt_forward_host": (C.c_int, [_P, _U64P, _U64P]),
     "xntt_inverse_host": (C.c_int, [_P, _U64P, _U64P]),
@@ -172,6 +173,9 @@ class Plan:
 
     def inverse(self, dst, src, stream=0):
         self._call("xntt_inverse", dst, src, stream)
+
+    def forward_multiply(self, dst, src, b_mont, stream=0):
+        self._call("xntt_forward_multiply", dst, src, b_mont, stream)
 
     def run_pass(self, index, inverse, dst, src, stream=0):
         self._call("xntt_run_pass", index, 1 if inverse else 0, dst, src, stream)

@@ -58,6 +58,8 @@ struct PassParams {
   u32 rows;            // row mode: number of valid rows in the buffer (tiles may be ragged)
   Tw scale;
   FieldConsts field;
+  const u64* pointwise;  // forward row pass: multiply output word i by pointwise[i] * 2^-64 (fused
+                         // PAdic64::multiply_normalize against a to_montgomery'd spectrum), or null
 };
 
 // Input of the on-device table generator: out[idx] = scale * root^e(idx), Montgomery pair.

@@ -289,10 +289,16 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < Cfg::C; ++c) {
-          if constexpr (TWIST)
+          if constexpr (TWIST) {
             x[r][c] = apply_twist<F, Cfg::LOGN>(f, prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
-          else
+          } else if (prm.pointwise != nullptr) {
+            // fused point-wise product of a polynomial multiply
+            // (examples/magic-series/gaussian-polynomial.hpp:201-212); the Montgomery product is canonical
+            const u64 b = (prm.pointwise + (gdst - prm.dst))[gofs<Cfg>(prm, k0 + (r << LOGS), p, c)];
+            x[r][c] = f.mont(x[r][c], b, f.companion(b));
+          } else {
             x[r][c] = f.canon(x[r][c]);
+          }
         }
       gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
     } else {

@@ -128,7 +128,7 @@ int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int
 // One pass.  `count_override` (when non-zero) replaces the number of outer blocks / rows: the row
 // half of a sharded plan only holds 1/shard_count of them.
 int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* src, void* st,
-             u64 count_override) {
+             u64 count_override, const u64* pointwise = nullptr) {
   const PassDesc& ps = pl->passes[i];
   PassParams prm{};
   prm.src = src;
@@ -158,6 +158,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     if (rows == 0 || rows > 0xffffffffull) return XNTT_ERR_INVALID;
     prm.rows = (u32)rows;
     prm.scale_on = (inverse && pl->scale_on && pl->passes.size() == 1) ? 1u : 0u;
+    prm.pointwise = inverse ? nullptr : pointwise;
     grid = (unsigned)((rows + (1u << logw) - 1) >> logw);
   }
   BE(be::launch_pass(ps.logn, ps.col, inverse, prm, grid, st));
@@ -167,7 +168,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
 // passes [first, last) in forward order (reverse order for the inverse); the first executed pass
 // reads src, every later one works in place on dst.
 int run_range(const xntt_plan* pl, bool inverse, size_t first, size_t last, u64* dst, const u64* src, void* st,
-              bool shard_rows) {
+              bool shard_rows, const u64* pointwise = nullptr) {
   if (!dst || !src) return XNTT_ERR_INVALID;
   if (inverse ? !pl->inv : !pl->fwd) return XNTT_ERR_STATE;
   DeviceGuard g(pl->device);
@@ -181,7 +182,7 @@ int run_range(const xntt_plan* pl, bool inverse, size_t first, size_t last, u64*
       const u64 full = ps.col ? ((u64)pl->batch << ps.log_outer) : ((u64)pl->batch << (pl->log2_m - ps.logn));
       count = full / pl->shard_count;
     }
-    const int rc = run_pass(pl, i, inverse, dst, cur, st, count);
+    const int rc = run_pass(pl, i, inverse, dst, cur, st, count, pointwise);
     if (rc != XNTT_OK) return rc;
     cur = dst;
   }
@@ -410,6 +411,13 @@ int xntt_inverse(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* 
   if (!pl) return XNTT_ERR_INVALID;
   if (pl->shard_count > 1) return XNTT_ERR_STATE;
   return run_range(pl, true, 0, pl->passes.size(), (u64*)dst, (const u64*)src, stream, false);
+}
+
+int xntt_forward_multiply(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, const uint64_t* b_mont,
+                          void* stream) {
+  if (!pl || !b_mont) return XNTT_ERR_INVALID;
+  if (pl->shard_count > 1) return XNTT_ERR_STATE;
+  return run_range(pl, false, 0, pl->passes.size(), (u64*)dst, (const u64*)src, stream, false, (const u64*)b_mont);
 }
 
 int xntt_run_pass(const xntt_plan* pl, uint32_t pass, int inverse, uint64_t* dst, const uint64_t* src,

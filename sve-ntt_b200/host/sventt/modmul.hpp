@@ -52,6 +52,45 @@ class PAdic64 {
   static constexpr std::uint64_t subtract(std::uint64_t a, std::uint64_t b) { return modulus_type::subtract(a, b); }
 };
 
+// sventt::FixedPoint64<modulus_type> - the Shoup-style alternative modmul tag
+// (include/sventt/modmul/{scalar,sve}/fixed-point-64.hpp): to/from_montgomery are the identity,
+// precompute(b) = floor(b * 2^64 / N), multiply(a, b, bp) = a * b mod N.  As a layer tag it selects the
+// same device kernels (the transform computed is the same function); the scalar helpers follow the
+// reference so that mixed-tag compositions (tests/ntt-tests/iterative-scalar-radix2-two10.hpp) compile.
+template <class modulus_type_>
+class FixedPoint64 {
+  using u128 = unsigned __int128;
+
+ public:
+  using modulus_type = modulus_type_;
+  static constexpr std::uint64_t to_montgomery(std::uint64_t b) { return b; }
+  static constexpr std::uint64_t from_montgomery(std::uint64_t b) { return b; }
+  static constexpr std::uint64_t precompute(std::uint64_t b) {
+    return static_cast<std::uint64_t>((static_cast<u128>(b) << 64) / modulus_type::get_modulus());
+  }
+  static constexpr std::uint64_t multiply_normalize(std::uint64_t a, std::uint64_t b, std::uint64_t bp) {
+    constexpr std::uint64_t N = modulus_type::get_modulus();
+    const std::uint64_t q = static_cast<std::uint64_t>((static_cast<u128>(a) * bp) >> 64);
+    // a*b - q*N lies in [0, 2N): one conditional subtraction, carried out in 128 bits
+    u128 r = static_cast<u128>(a) * b - static_cast<u128>(q) * N;
+    if (r >= N) r -= N;
+    return static_cast<std::uint64_t>(r);
+  }
+  static constexpr std::uint64_t multiply_normalize(std::uint64_t a, std::uint64_t b) {
+    return multiply_normalize(a, b, precompute(b));
+  }
+  static constexpr std::uint64_t multiply(std::uint64_t a, std::uint64_t b, std::uint64_t bp) {
+    return multiply_normalize(a, b, bp);
+  }
+  static constexpr std::uint64_t multiply(std::uint64_t a, std::uint64_t b) { return multiply_normalize(a, b); }
+  static constexpr std::uint64_t add(std::uint64_t a, std::uint64_t b) { return modulus_type::add(a, b); }
+  static constexpr std::uint64_t subtract(std::uint64_t a, std::uint64_t b) { return modulus_type::subtract(a, b); }
+};
+template <class modulus_type>
+using FixedPoint64SVE = FixedPoint64<modulus_type>;
+template <class modulus_type>
+using FixedPoint64Scalar = FixedPoint64<modulus_type>;
+
 template <class modulus_type>
 using PAdic64SVE = PAdic64<modulus_type>;
 template <class modulus_type>

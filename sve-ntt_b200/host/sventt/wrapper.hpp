@@ -92,6 +92,12 @@ class NTT {
   void compute_inverse_async(std::uint64_t* dst, const std::uint64_t* src, void* stream) const {
     detail::check(xntt_inverse(plan_, dst, src, stream), "compute_inverse");
   }
+  // forward transform fused with the point-wise multiply_normalize against a to_montgomery'd spectrum
+  // (the loop at examples/magic-series/gaussian-polynomial.hpp:201-212); device pointers
+  void compute_forward_multiply_async(std::uint64_t* dst, const std::uint64_t* src, const std::uint64_t* b_mont,
+                                      void* stream) const {
+    detail::check(xntt_forward_multiply(plan_, dst, src, b_mont, stream), "compute_forward_multiply");
+  }
   const xntt_plan* plan() const { return plan_; }
 
  private:

@@ -45,6 +45,16 @@ using L = RadixTwoSVELayer<modmul_type, m, n, f>;
 using kernel_type = IterativeNTT<modulus_type, m, L<one << 10>, L<one << 9>, L<one << 8>, L<one << 7>, L<one << 6>,
                                  L<one << 5>, L<one << 4>, L<one << 3>, L<one << 2>, L<one << 1, m>>;
 }  // namespace it_r2
+// ---- tests/ntt-tests/iterative-scalar-radix2-two10.hpp shape: PAdic64 and FixedPoint64 layers mixed
+namespace it_mixed {
+constexpr std::uint64_t m{one << 10};
+using fp = FixedPoint64Scalar<modulus_type>;
+using pa = PAdic64Scalar<modulus_type>;
+using kernel_type =
+    IterativeNTT<modulus_type, m, RadixTwoScalarLayer<pa, m, one << 10>, RadixTwoScalarLayer<fp, m, one << 9>,
+                 RadixFourScalarLayer<pa, m, one << 8>, RadixFourScalarLayer<fp, m, one << 6>,
+                 RadixEightScalarLayer<pa, m, one << 4>, RadixTwoScalarLayer<fp, m, one << 1, m>>;
+}  // namespace it_mixed
 // ---- tests/ntt-tests/iterative-sve-radix4-two12.hpp
 namespace it_r4 {
 constexpr std::uint64_t m{one << 12};
@@ -203,6 +213,7 @@ int main(int argc, char** argv) {
   const bool big = argc > 1 && std::string{argv[1]} == "--big";
   try {
     both<it_r2::kernel_type>("iterative, SVE, radix-2");
+    both<it_mixed::kernel_type>("iterative, scalar, mixed modmul tags");
     both<it_r4::kernel_type>("iterative, SVE, radix-4");
     both<it_r8::kernel_type>("iterative, SVE, radix-8");
     both<it_r248::kernel_type>("iterative, scalar, radix-2,4,8");
@@ -217,6 +228,9 @@ int main(int argc, char** argv) {
     static_assert(modulus_type::get_montgomery_inverse() == UINT64_C(0x4000039180000001));
     static_assert(P::to_montgomery(1) == UINT64_C(0x3917fffffff));
     static_assert(P::from_montgomery(P::to_montgomery(12345)) == 12345);
+    using FP = FixedPoint64<modulus_type>;
+    static_assert(FP::multiply(0xfffffc6e80000000ull, 0xfffffc6e80000000ull) == 1);  // (-1)^2
+    static_assert(FP::multiply(P::to_montgomery(7), 3) == modulus_type::multiply(P::to_montgomery(7), 3));
     static_assert(modulus_type::multiply(modulus_type::get_root_forward(one << 31), modulus_type::get_root_inverse(one << 31)) == 1);
     bool threw = false;
     try {

@@ -238,3 +238,24 @@ def test_golden_full_vectors_all_moduli(emu, golden):
         assert [f"{int(v):016x}" for v in out] == case["forward"]
         plan.inverse(out.ctypes.data, a.ctypes.data)
         assert [f"{int(v):016x}" for v in out] == case["inverse"]
+
+
+@pytest.mark.parametrize("L,splits,N,g", [(8, None, P0, G0), (14, None, P0, G0), (13, [9, 4], 0x3A00000000000001, 3),
+                                         (12, None, 0xFFFFFFFF00000001, 7), (16, [5, 5, 6], P0, G0)])
+def test_fused_forward_multiply(emu, oracle, L, splits, N, g):
+    """xntt_forward_multiply == compute_forward followed by the multiply_normalize loop
+    (examples/magic-series/gaussian-polynomial.hpp:196-212), for every plan shape."""
+    m = 1 << L
+    rng = np.random.default_rng(L)
+    a = rng.integers(0, N, m, dtype=np.uint64)
+    b = rng.integers(0, N, m, dtype=np.uint64)
+    plan = emu.plan(L, modulus=N, generator=g, splits=splits)
+    fb = np.empty_like(b)
+    plan.forward(fb.ctypes.data, b.ctypes.data)
+    plan.to_montgomery(fb.ctypes.data, fb.ctypes.data, m)
+    fused = np.empty_like(a)
+    plan.forward_multiply(fused.ctypes.data, a.ctypes.data, fb.ctypes.data)
+    want = oracle.pointwise_mul(oracle.ntt_forward(a, N, g), oracle.ntt_forward(b, N, g), N)
+    assert np.array_equal(fused, want)
+    plan.inverse(fused.ctypes.data, fused.ctypes.data)
+    assert np.array_equal(fused, oracle.ntt_inverse(want, N, g))

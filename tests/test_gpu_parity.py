@@ -181,6 +181,11 @@ def test_polynomial_multiply(cuda_lib, oracle):
     want = oracle.ntt_inverse(oracle.pointwise_mul(oracle.ntt_forward(a, P0, G0), oracle.ntt_forward(b, P0, G0), P0),
                               P0, G0)
     assert np.array_equal(host(da), want)
+    # the fused form (point-wise product inside the last forward pass) gives the same words
+    da2 = dev(a)
+    plan.forward_multiply(da2.data_ptr(), da2.data_ptr(), db.data_ptr(), stream())
+    plan.inverse(da2.data_ptr(), da2.data_ptr(), stream())
+    assert np.array_equal(host(da2), want)
     # a few coefficients by schoolbook convolution
     ai, bi = [int(v) for v in a[:64]], [int(v) for v in b[:64]]
     for k in (0, 1, 17, 63):
@@ -320,3 +325,26 @@ def test_other_moduli(cuda_lib, oracle, N, g):
         plan.multiply_normalize(prod.data_ptr(), dev(got).data_ptr(), bm.data_ptr(), a.size, stream())
         assert np.array_equal(host(prod), oracle.pointwise_mul(got, a, N))
         plan.close()
+
+
+@pytest.mark.parametrize("L,splits,N,g", [(14, None, P0, G0), (13, [9, 4], 0x3A00000000000001, 3), (20, None, P0, G0),
+                                         (24, None, P0, G0)])
+def test_fused_forward_multiply(cuda_lib, oracle, L, splits, N, g):
+    import torch
+    m = 1 << L
+    rng = np.random.default_rng(L)
+    a = rng.integers(0, N, m, dtype=np.uint64)
+    b = rng.integers(0, N, m, dtype=np.uint64)
+    plan = cuda_lib.plan(L, modulus=N, generator=g, splits=splits)
+    da, db = dev(a), dev(b)
+    fb, unfused, fused = torch.empty_like(db), torch.empty_like(da), torch.empty_like(da)
+    plan.forward(fb.data_ptr(), db.data_ptr(), stream())
+    plan.to_montgomery(fb.data_ptr(), fb.data_ptr(), m, stream())
+    plan.forward(unfused.data_ptr(), da.data_ptr(), stream())
+    plan.multiply_normalize(unfused.data_ptr(), unfused.data_ptr(), fb.data_ptr(), m, stream())
+    plan.forward_multiply(fused.data_ptr(), da.data_ptr(), fb.data_ptr(), stream())
+    assert torch.equal(fused, unfused)
+    if L <= 20:
+        want = oracle.pointwise_mul(oracle.ntt_forward(a, N, g), oracle.ntt_forward(b, N, g), N)
+        assert np.array_equal(host(fused), want)
+    plan.close()
