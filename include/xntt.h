@@ -109,6 +109,26 @@ int xntt_shard_forward_rows(const xntt_plan* plan, uint64_t* dst, const uint64_t
 int xntt_shard_inverse_rows(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
 int xntt_shard_inverse_cols(const xntt_plan* plan, uint64_t* dst, const uint64_t* src, void* stream);
 
+/* Exchange-friendly variants.  The local column block is cut into nchunks
+ * column sub-blocks of w = n1 / (shard_count * nchunks) columns.
+ *   forward_cols_chunk : column pass + twiddle of chunk c, written compactly at
+ *                        tiles + c * n0 * w as [n0][w] - shard_count contiguous messages, so the
+ *                        caller can start that chunk's all-to-all while the next chunk computes
+ *   forward_rows_tiled : after all chunks arrived (message from rank s of chunk c at
+ *                        tiles + c * n0 * w + s * (n0 / shard_count) * w): the row half, reading that
+ *                        tiled layout in place of a separate unpacking pass; dst in natural order
+ *   inverse_rows_tiled : row half of the inverse, leaving its result in the tiled layout (work: scratch
+ *                        of m / shard_count words, needed for plans of three passes, else may be null)
+ *   inverse_cols_chunk : column pass of chunk c from the compact chunk layout into the column block */
+int xntt_shard_forward_cols_chunk(const xntt_plan* plan, uint64_t* tiles, const uint64_t* src, uint32_t chunk,
+                                  uint32_t nchunks, void* stream);
+int xntt_shard_forward_rows_tiled(const xntt_plan* plan, uint64_t* dst, const uint64_t* tiles, uint32_t nchunks,
+                                  void* stream);
+int xntt_shard_inverse_rows_tiled(const xntt_plan* plan, uint64_t* tiles, const uint64_t* src, uint64_t* work,
+                                  uint32_t nchunks, void* stream);
+int xntt_shard_inverse_cols_chunk(const xntt_plan* plan, uint64_t* dst, const uint64_t* tiles, uint32_t chunk,
+                                  uint32_t nchunks, void* stream);
+
 /* PAdic64 element-wise helpers on device buffers (count words each):
  *   to_montgomery      : dst[i] = src[i] * 2^64 mod p     (modmul/sve/p-adic-64.hpp:19-22)
  *   from_montgomery    : dst[i] = src[i] * 2^-64 mod p    (p-adic-64.hpp:24-38, canonical result)

@@ -63,6 +63,10 @@ SYMBOLS = {
     "xntt_shard_forward_rows": (C.c_int, [_P, _U64P, _U64P, _P]),
     "xntt_shard_inverse_rows": (C.c_int, [_P, _U64P, _U64P, _P]),
     "xntt_shard_inverse_cols": (C.c_int, [_P, _U64P, _U64P, _P]),
+    "xntt_shard_forward_cols_chunk": (C.c_int, [_P, _U64P, _U64P, C.c_uint32, C.c_uint32, _P]),
+    "xntt_shard_forward_rows_tiled": (C.c_int, [_P, _U64P, _U64P, C.c_uint32, _P]),
+    "xntt_shard_inverse_rows_tiled": (C.c_int, [_P, _U64P, _U64P, _U64P, C.c_uint32, _P]),
+    "xntt_shard_inverse_cols_chunk": (C.c_int, [_P, _U64P, _U64P, C.c_uint32, C.c_uint32, _P]),
     "xntt_to_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
     "xntt_from_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
     "xntt_multiply_normalize": (C.c_int, [_P, _U64P, _U64P, _U64P, C.c_size_t, _P]),
@@ -197,6 +201,18 @@ class Plan:
 
     def shard_inverse_cols(self, dst, src, stream=0):
         self._call("xntt_shard_inverse_cols", dst, src, stream)
+
+    def shard_forward_cols_chunk(self, tiles, src, chunk, nchunks, stream=0):
+        self._call("xntt_shard_forward_cols_chunk", tiles, src, chunk, nchunks, stream)
+
+    def shard_forward_rows_tiled(self, dst, tiles, nchunks, stream=0):
+        self._call("xntt_shard_forward_rows_tiled", dst, tiles, nchunks, stream)
+
+    def shard_inverse_rows_tiled(self, tiles, src, work, nchunks, stream=0):
+        self._call("xntt_shard_inverse_rows_tiled", tiles, src, work, nchunks, stream)
+
+    def shard_inverse_cols_chunk(self, dst, tiles, chunk, nchunks, stream=0):
+        self._call("xntt_shard_inverse_cols_chunk", dst, tiles, chunk, nchunks, stream)
 
     def to_montgomery(self, dst, src, count, stream=0):
         self._call("xntt_to_montgomery", dst, src, count, stream)

@@ -23,7 +23,8 @@ int stream_sync(void* stream);
 int pointer_is_device(const void* p, int* is_device);
 const char* last_error();
 
-int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void* stream);
+// map = true: use prm.smap / prm.dmap (generalised addressing; built for kP0 only)
+int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid, void* stream);
 // the field is chosen by fc.p: kP0 runs the kernels with the modulus baked in, anything else the
 // runtime-modulus kernels (PassParams carries its own copy in prm.field)
 int launch_gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t,

@@ -204,10 +204,19 @@ int pointer_is_device(const void* p, int* is_device) {
 }
 const char* last_error() { return g_err.c_str(); }
 
-int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void* stream) {
+int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (prm.field.p == kP0) {
+  if (map) {
+    if (prm.field.p != kP0) {
+      g_err = "address-mapped kernels are built for the production modulus only";
+      return 1;
+    }
+    if (col)
+      e = inverse ? launch_inv_col_map(logn, prm, grid, st) : launch_fwd_col_map(logn, prm, grid, st);
+    else
+      e = inverse ? launch_inv_row_map(logn, prm, grid, st) : launch_fwd_row_map(logn, prm, grid, st);
+  } else if (prm.field.p == kP0) {
     if (col)
       e = inverse ? launch_inv_col(logn, prm, grid, st) : launch_fwd_col(logn, prm, grid, st);
     else

@@ -11,16 +11,21 @@ cudaError_t launch_fwd_row(int logn, const PassParams& prm, unsigned grid, cudaS
 cudaError_t launch_inv_row(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+// kP0 kernels with generalised src/dst address maps (passes next to the all-to-all of a sharded plan)
+cudaError_t launch_fwd_row_map(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_row_map(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_col_map(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_col_map(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 
-template <class F, int LOGN, bool COL, bool INV>
+template <class F, int LOGN, bool COL, bool INV, bool MAP = false>
 cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
   constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
-  auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, COL>;
+  auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, COL, MAP>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
@@ -34,5 +39,8 @@ cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
 #define XNTT_CASE(F, L, COL, INV) \
   case L:                         \
     return launch_one<F, L, COL, INV>(prm, grid, st);
+#define XNTT_CASE_MAP(F, L, COL, INV) \
+  case L:                             \
+    return launch_one<F, L, COL, INV, true>(prm, grid, st);
 
 }  // namespace xntt

@@ -36,6 +36,16 @@ constexpr int tile_c(int logn) { return (!XNTT_FORCE_C1 && tile_logw(logn) >= 1)
 // The production prime of the reference README (README.md:19): 2^64 - 1827*2^31 + 1.
 constexpr u64 kP0 = 0xfffffc6e80000001ULL;
 
+// Generalised addressing of the transform index k (used by the passes next to the all-to-all of a
+// sharded plan, where the exchange leaves / expects the data tiled): k is cut into three bit fields
+// [0, b1), [b1, b2), [b2, ...) with their own strides; `outer` is the stride of the outer block (column
+// mode) or of a row (row mode).
+struct StrideMap {
+  u64 s0, s1, s2;
+  u64 outer;
+  u32 b1, b2;
+};
+
 // Field constants of a runtime modulus (ignored by the kernels specialised for kP0).
 struct FieldConsts {
   u64 p;     // modulus
@@ -58,6 +68,7 @@ struct PassParams {
   u32 rows;            // row mode: number of valid rows in the buffer (tiles may be ragged)
   Tw scale;
   FieldConsts field;
+  StrideMap smap, dmap;  // MAP kernels only: address maps of src and dst
   const u64* pointwise;  // forward row pass: multiply output word i by pointwise[i] * 2^-64 (fused
                          // PAdic64::multiply_normalize against a to_montgomery'd spectrum), or null
 };

@@ -61,10 +61,10 @@ __device__ __forceinline__ int swz(int k) {
   return k ^ ((k >> 3) & Slot<C>::kSwzMask);
 }
 
-template <int LOGN_, int LOGW_, int C_, bool COL_>
+template <int LOGN_, int LOGW_, int C_, bool COL_, bool MAP_ = false>
 struct PassCfg {
   static constexpr int LOGN = LOGN_, LOGW = LOGW_, C = C_;
-  static constexpr bool COL = COL_;
+  static constexpr bool COL = COL_, MAP = MAP_;
   static constexpr int N = 1 << LOGN, W = 1 << LOGW;
   static constexpr int NP = W / C;  // column groups per tile
   static constexpr int LOGNP = LOGW - (C == 2 ? 1 : 0);
@@ -110,13 +110,26 @@ __device__ __forceinline__ void smem_store(typename Slot<Cfg::C>::type* sm, int 
   }
 }
 
+__device__ __forceinline__ u64 map_k(const StrideMap& m, int k) {
+  const u32 uk = (u32)k;
+  return (u64)(uk & ((1u << m.b1) - 1u)) * m.s0 + (u64)((uk >> m.b1) & ((1u << (m.b2 - m.b1)) - 1u)) * m.s1 +
+         (u64)(uk >> m.b2) * m.s2;
+}
+
 // Global addressing of element (k, column group p, lane c) relative to the tile base.
 template <class Cfg>
-__device__ __forceinline__ u64 gofs(const PassParams& prm, int k, int p, int c) {
-  if constexpr (Cfg::COL)
-    return (u64)k * prm.inner + (u64)(p * Cfg::C + c);
-  else
-    return ((u64)(p * Cfg::C + c) << Cfg::LOGN) + (u64)k;
+__device__ __forceinline__ u64 gofs(const PassParams& prm, const StrideMap& map, int k, int p, int c) {
+  if constexpr (Cfg::MAP) {
+    if constexpr (Cfg::COL)
+      return map_k(map, k) + (u64)(p * Cfg::C + c);
+    else
+      return (u64)(p * Cfg::C + c) * map.outer + map_k(map, k);
+  } else {
+    if constexpr (Cfg::COL)
+      return (u64)k * prm.inner + (u64)(p * Cfg::C + c);
+    else
+      return ((u64)(p * Cfg::C + c) << Cfg::LOGN) + (u64)k;
+  }
 }
 
 template <class Cfg, int R>
@@ -127,11 +140,11 @@ __device__ __forceinline__ void gmem_load(const PassParams& prm, const u64* base
     for (int r = 0; r < R; ++r) {
       const int k = k0 + (r << logs);
       if constexpr (Cfg::C == 2) {
-        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(base + gofs<Cfg>(prm, k, p, 0));
+        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(base + gofs<Cfg>(prm, prm.smap, k, p, 0));
         x[r][0] = v.x;
         x[r][1] = v.y;
       } else {
-        x[r][0] = base[gofs<Cfg>(prm, k, p, 0)];
+        x[r][0] = base[gofs<Cfg>(prm, prm.smap, k, p, 0)];
       }
     }
   } else {
@@ -140,7 +153,7 @@ __device__ __forceinline__ void gmem_load(const PassParams& prm, const u64* base
     for (int c = 0; c < Cfg::C; ++c) {
       const bool ok = row0 + (u32)(p * Cfg::C + c) < prm.rows;
 #pragma unroll
-      for (int r = 0; r < R; ++r) x[r][c] = ok ? base[gofs<Cfg>(prm, k0 + (r << logs), p, c)] : 0ull;
+      for (int r = 0; r < R; ++r) x[r][c] = ok ? base[gofs<Cfg>(prm, prm.smap, k0 + (r << logs), p, c)] : 0ull;
     }
   }
 }
@@ -152,10 +165,10 @@ __device__ __forceinline__ void gmem_store(const PassParams& prm, u64* base, u32
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if constexpr (Cfg::C == 2)
-        *reinterpret_cast<ulonglong2*>(base + gofs<Cfg>(prm, k0 + (r << logs), p, 0)) =
+        *reinterpret_cast<ulonglong2*>(base + gofs<Cfg>(prm, prm.dmap, k0 + (r << logs), p, 0)) =
             make_ulonglong2(x[r][0], x[r][1]);
       else
-        base[gofs<Cfg>(prm, k0 + (r << logs), p, 0)] = x[r][0];
+        base[gofs<Cfg>(prm, prm.dmap, k0 + (r << logs), p, 0)] = x[r][0];
     }
   } else {
 #pragma unroll
@@ -165,11 +178,11 @@ __device__ __forceinline__ void gmem_store(const PassParams& prm, u64* base, u32
           // a thread owns R consecutive outputs of this row: 128-bit stores
 #pragma unroll
           for (int r = 0; r + 1 < R; r += 2)
-            *reinterpret_cast<ulonglong2*>(base + gofs<Cfg>(prm, k0 + r, p, c)) =
+            *reinterpret_cast<ulonglong2*>(base + gofs<Cfg>(prm, prm.dmap, k0 + r, p, c)) =
                 make_ulonglong2(x[r][c], x[r + 1][c]);
         } else {
 #pragma unroll
-          for (int r = 0; r < R; ++r) base[gofs<Cfg>(prm, k0 + (r << logs), p, c)] = x[r][c];
+          for (int r = 0; r < R; ++r) base[gofs<Cfg>(prm, prm.dmap, k0 + (r << logs), p, c)] = x[r][c];
         }
       }
     }
@@ -294,7 +307,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
           } else if (prm.pointwise != nullptr) {
             // fused point-wise product of a polynomial multiply
             // (examples/magic-series/gaussian-polynomial.hpp:201-212); the Montgomery product is canonical
-            const u64 b = (prm.pointwise + (gdst - prm.dst))[gofs<Cfg>(prm, k0 + (r << LOGS), p, c)];
+            const u64 b = (prm.pointwise + (gdst - prm.dst))[gofs<Cfg>(prm, prm.dmap, k0 + (r << LOGS), p, c)];
             x[r][c] = f.mont(x[r][c], b, f.companion(b));
           } else {
             x[r][c] = f.canon(x[r][c]);
@@ -375,27 +388,43 @@ __device__ __forceinline__ void run_stages(const PassParams& prm, typename Slot<
     (fwd_stage<F, Cfg, TWIST, Js>(prm, sm, gsrc, gdst, col0, row0), ...);
 }
 
+// Where tile number `tile` starts in src and dst, and which global column / row it begins with.
+template <class Cfg>
+__device__ __forceinline__ void tile_origin(const PassParams& prm, u32 tile, u64& sbase, u64& dbase, u32& col0,
+                                            u32& row0) {
+  if constexpr (Cfg::COL) {
+    const u32 o = tile / prm.tiles_per_outer, cb = tile - o * prm.tiles_per_outer;
+    if constexpr (Cfg::MAP) {
+      sbase = (u64)o * prm.smap.outer + (u64)cb * Cfg::W;
+      dbase = (u64)o * prm.dmap.outer + (u64)cb * Cfg::W;
+    } else {
+      sbase = dbase = (u64)o * prm.outer_stride + (u64)cb * Cfg::W;
+    }
+    col0 = prm.twist_col0 + cb * Cfg::W;
+  } else {
+    row0 = tile << Cfg::LOGW;
+    if constexpr (Cfg::MAP) {
+      sbase = (u64)row0 * prm.smap.outer;
+      dbase = (u64)row0 * prm.dmap.outer;
+    } else {
+      sbase = dbase = ((u64)tile << (Cfg::LOGN + Cfg::LOGW));
+    }
+  }
+}
+
 #if !defined(XNTT_HOST_EMU)
-template <class F, int LOGN, int LOGW, int C, bool COL, bool INVERSE, bool TWIST>
+template <class F, int LOGN, int LOGW, int C, bool COL, bool INVERSE, bool TWIST, bool MAP = false>
 __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_constant__ PassParams prm) {
-  typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
+  typedef PassCfg<LOGN, LOGW, C, COL, MAP> Cfg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto* sm = reinterpret_cast<typename Slot<C>::type*>(smem_raw);
   const u32 tile = blockIdx.x;
-  u64 base;
+  u64 sbase, dbase;
   u32 col0 = 0, row0 = 0;
-  if constexpr (COL) {
-    const u32 o = tile / prm.tiles_per_outer, cb = tile - o * prm.tiles_per_outer;
-    base = (u64)o * prm.outer_stride + (u64)cb * Cfg::W;
-    col0 = prm.twist_col0 + cb * Cfg::W;
-  } else {
-    base = ((u64)tile << (LOGN + LOGW));
-    row0 = tile << LOGW;
-  }
-  run_stages<F, Cfg, INVERSE, TWIST>(prm, sm, prm.src + base, prm.dst + base, col0, row0,
+  tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
+  run_stages<F, Cfg, INVERSE, TWIST>(prm, sm, prm.src + sbase, prm.dst + dbase, col0, row0,
                                      std::make_integer_sequence<int, Cfg::NS>{});
 }
-
 #endif  // !XNTT_HOST_EMU
 
 }  // namespace xntt

@@ -161,7 +161,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.pointwise = inverse ? nullptr : pointwise;
     grid = (unsigned)((rows + (1u << logw) - 1) >> logw);
   }
-  BE(be::launch_pass(ps.logn, ps.col, inverse, prm, grid, st));
+  BE(be::launch_pass(ps.logn, ps.col, inverse, false, prm, grid, st));
   return XNTT_OK;
 }
 
@@ -204,6 +204,113 @@ int host_roundtrip(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, bool
   brc = be::stream_sync(nullptr);
   if (rc == XNTT_OK && brc != 0) rc = be_fail(brc);
   return rc;
+}
+
+// ---- sharded plans: exchange-friendly ("tiled") variants -----------------------------------------
+// Notation: G ranks, K chunks, m = n0 * n1, w = n1 / (G * K) columns per chunk.
+//   chunk layout  : chunk c of a rank's column block, compact, [n0][w] row-major = G contiguous
+//                   messages of (n0/G) * w words (message s = rows of rank s)
+//   tiled layout  : what a rank holds after the all-to-all of every chunk: [K][G][n0/G][w]
+// The column pass writes (reads) chunk layout; the first (last) local pass of the row half reads
+// (writes) the tiled layout directly through a StrideMap, so no separate (un)packing pass exists.
+StrideMap natural_map(const xntt_plan* pl, const PassDesc& ps) {
+  StrideMap m{};
+  m.b1 = m.b2 = 31;
+  if (ps.col) {
+    m.s0 = 1ull << ps.log_inner;
+    m.outer = 1ull << (ps.log_inner + ps.logn);
+  } else {
+    m.s0 = 1;
+    m.outer = 1ull << ps.logn;
+  }
+  (void)pl;
+  return m;
+}
+
+int log2u(u64 v) {
+  int l = 0;
+  while ((1ull << l) < v) ++l;
+  return l;
+}
+
+// map of pass 1's transform index onto the tiled layout
+int tiled_map(const xntt_plan* pl, u32 nchunks, StrideMap& out) {
+  const PassDesc& p1 = pl->passes[1];
+  const u64 G = pl->shard_count, K = nchunks;
+  const u64 n0 = 1ull << pl->passes[0].logn, n1 = (1ull << pl->log2_m) / n0;
+  if (K == 0 || (K & (K - 1)) || n1 % (G * K)) return XNTT_ERR_INVALID;
+  const u64 w = n1 / (G * K);
+  StrideMap m{};
+  if (p1.col) {
+    const u64 n1b = 1ull << p1.log_inner;  // contiguous inner run of pass 1
+    if (w % n1b) return XNTT_ERR_UNSUPPORTED;
+    m.s0 = n1b;
+    m.b1 = (u32)log2u(w / n1b);
+  } else {
+    m.s0 = 1;
+    m.b1 = (u32)log2u(w);
+  }
+  m.b2 = m.b1 + (u32)log2u(K);
+  m.s1 = n0 * w;          // next chunk
+  m.s2 = (n0 / G) * w;    // next source rank inside a chunk
+  m.outer = w;            // next local row
+  out = m;
+  return XNTT_OK;
+}
+
+int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* src, const StrideMap& smap,
+                    const StrideMap& dmap, u64 units, u32 tiles_per_outer, u32 twist_col0, void* st) {
+  const PassDesc& ps = pl->passes[i];
+  PassParams prm{};
+  prm.src = src;
+  prm.dst = dst;
+  prm.tw = inverse ? ps.inv_tw : ps.fwd_tw;
+  prm.scale = pl->scale;
+  prm.field = pl->field;
+  prm.smap = smap;
+  prm.dmap = dmap;
+  const int logw = tile_logw(ps.logn);
+  unsigned grid;
+  if (ps.col) {
+    prm.tiles_per_outer = tiles_per_outer;
+    prm.twist_lo = inverse ? ps.inv_lo : ps.fwd_lo;
+    prm.twist_hi = inverse ? ps.inv_hi : ps.fwd_hi;
+    prm.twist_shift = (u32)ps.twist_shift;
+    prm.twist_col0 = twist_col0;
+    const u64 tiles = units * tiles_per_outer;
+    if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
+    grid = (unsigned)tiles;
+  } else {
+    prm.rows = (u32)units;
+    prm.scale_on = 0;
+    grid = (unsigned)((units + (1u << logw) - 1) >> logw);
+  }
+  BE(be::launch_pass(ps.logn, ps.col, inverse, true, prm, grid, st));
+  return XNTT_OK;
+}
+
+int shard_cols_chunk(const xntt_plan* pl, bool inverse, u64* dst, const u64* src, u32 chunk, u32 nchunks, void* st) {
+  if (!pl || !dst || !src || pl->shard_count < 2) return XNTT_ERR_STATE;
+  if (inverse ? !pl->inv : !pl->fwd) return XNTT_ERR_STATE;
+  if (pl->batch != 1 || nchunks == 0 || (nchunks & (nchunks - 1)) || chunk >= nchunks) return XNTT_ERR_INVALID;
+  const PassDesc& p0 = pl->passes[0];
+  const u64 G = pl->shard_count, n0 = 1ull << p0.logn, n1 = (1ull << pl->log2_m) / n0;
+  if (n1 % (G * nchunks)) return XNTT_ERR_INVALID;
+  const u64 w = n1 / (G * nchunks), block = n1 / G;
+  if (w < (1ull << tile_logw(p0.logn))) return XNTT_ERR_UNSUPPORTED;
+  DeviceGuard g(pl->device);
+  if (!g.ok) return be_fail(1);
+  StrideMap full{}, compact{};
+  full.b1 = full.b2 = compact.b1 = compact.b2 = 31;
+  full.s0 = block;
+  full.outer = n0 * block;
+  compact.s0 = w;
+  compact.outer = n0 * w;
+  const u32 tpo = (u32)(w >> tile_logw(p0.logn));
+  const u32 col0 = (u32)(block * pl->shard_rank + w * chunk);
+  if (!inverse)  // block -> chunk layout
+    return run_pass_mapped(pl, 0, false, dst + n0 * w * chunk, src + w * chunk, full, compact, 1, tpo, col0, st);
+  return run_pass_mapped(pl, 0, true, dst + w * chunk, src + n0 * w * chunk, compact, full, 1, tpo, col0, st);
 }
 
 }  // namespace
@@ -442,6 +549,57 @@ int xntt_shard_inverse_rows(const xntt_plan* pl, uint64_t* dst, const uint64_t* 
 int xntt_shard_inverse_cols(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, void* stream) {
   if (!pl || pl->shard_count < 2) return XNTT_ERR_STATE;
   return run_range(pl, true, 0, 1, (u64*)dst, (const u64*)src, stream, false);
+}
+
+int xntt_shard_forward_cols_chunk(const xntt_plan* pl, uint64_t* tiles, const uint64_t* src, uint32_t chunk,
+                                  uint32_t nchunks, void* stream) {
+  return shard_cols_chunk(pl, false, (u64*)tiles, (const u64*)src, chunk, nchunks, stream);
+}
+int xntt_shard_inverse_cols_chunk(const xntt_plan* pl, uint64_t* dst, const uint64_t* tiles, uint32_t chunk,
+                                  uint32_t nchunks, void* stream) {
+  return shard_cols_chunk(pl, true, (u64*)dst, (const u64*)tiles, chunk, nchunks, stream);
+}
+int xntt_shard_forward_rows_tiled(const xntt_plan* pl, uint64_t* dst, const uint64_t* tiles, uint32_t nchunks,
+                                  void* stream) {
+  if (!pl || !dst || !tiles || pl->shard_count < 2) return XNTT_ERR_STATE;
+  if (!pl->fwd) return XNTT_ERR_STATE;
+  if (pl->batch != 1) return XNTT_ERR_INVALID;
+  StrideMap tm;
+  int rc = tiled_map(pl, nchunks, tm);
+  if (rc != XNTT_OK) return rc;
+  DeviceGuard g(pl->device);
+  if (!g.ok) return be_fail(1);
+  const PassDesc& p1 = pl->passes[1];
+  const u64 rows0 = (1ull << pl->passes[0].logn) / pl->shard_count;  // local rows of the n0 x n1 matrix
+  const u64 units = p1.col ? rows0 : rows0;  // pass 1: one outer block (column mode) or one row per local row
+  const u32 tpo = p1.col ? (u32)((1ull << p1.log_inner) >> tile_logw(p1.logn)) : 0u;
+  rc = run_pass_mapped(pl, 1, false, (u64*)dst, (const u64*)tiles, tm, natural_map(pl, p1), units, tpo, 0, stream);
+  if (rc != XNTT_OK) return rc;
+  if (pl->passes.size() > 2)
+    return run_range(pl, false, 2, pl->passes.size(), (u64*)dst, (const u64*)dst, stream, true);
+  return XNTT_OK;
+}
+int xntt_shard_inverse_rows_tiled(const xntt_plan* pl, uint64_t* tiles, const uint64_t* src, uint64_t* work,
+                                  uint32_t nchunks, void* stream) {
+  if (!pl || !tiles || !src || pl->shard_count < 2) return XNTT_ERR_STATE;
+  if (!pl->inv) return XNTT_ERR_STATE;
+  if (pl->batch != 1) return XNTT_ERR_INVALID;
+  StrideMap tm;
+  int rc = tiled_map(pl, nchunks, tm);
+  if (rc != XNTT_OK) return rc;
+  DeviceGuard g(pl->device);
+  if (!g.ok) return be_fail(1);
+  const u64* cur = (const u64*)src;
+  if (pl->passes.size() > 2) {
+    if (!work) return XNTT_ERR_INVALID;
+    rc = run_range(pl, true, 2, pl->passes.size(), (u64*)work, cur, stream, true);
+    if (rc != XNTT_OK) return rc;
+    cur = (const u64*)work;
+  }
+  const PassDesc& p1 = pl->passes[1];
+  const u64 rows0 = (1ull << pl->passes[0].logn) / pl->shard_count;
+  const u32 tpo = p1.col ? (u32)((1ull << p1.log_inner) >> tile_logw(p1.logn)) : 0u;
+  return run_pass_mapped(pl, 1, true, (u64*)tiles, cur, natural_map(pl, p1), tm, rows0, tpo, 0, stream);
 }
 
 int xntt_forward_host(const xntt_plan* pl, uint64_t* dst, const uint64_t* src) {

@@ -10,6 +10,10 @@ Layout, m = n0 * n1 viewed as an n0 x n1 row-major matrix, G ranks:
 forward  = column passes + twiddle (local) -> all-to-all of (n0/G x n1/G) tiles -> row passes (local)
 inverse  = row passes -> all-to-all -> column passes; back in the column-block layout.
 
+Pipelining: the column block is processed in K column chunks; chunk c's all-to-all (async, NCCL's
+own stream) runs while chunk c+1 computes, and the row half reads the received tiles in place
+(xntt_shard_*_tiled), so there is no separate pack/unpack pass over memory.
+
 torch.distributed is plumbing here (NCCL all_to_all_single over NVLink on the box, gloo in the CPU
 tests); the compute is libxntt's xntt_shard_* entry points.
 """
@@ -18,41 +22,83 @@ import torch.distributed as dist
 
 
 class ShardedNTT:
-    def __init__(self, library, log2_m, world, rank, device=-1, splits=None, group=None, inverse_factor=None):
+    def __init__(self, library, log2_m, world, rank, device=-1, splits=None, group=None, inverse_factor=None,
+                 chunks=None, modulus=None, generator=None):
         self.world, self.rank, self.group = world, rank, group
+        kw = {}
+        if modulus is not None:
+            kw.update(modulus=modulus, generator=generator)
         self.plan = library.plan(log2_m, splits=splits, shard_count=world, shard_rank=rank, device=device,
-                                 inverse_factor=inverse_factor)
+                                 inverse_factor=inverse_factor, **kw)
         self.splits = self.plan.splits
         self.n0 = 1 << self.splits[0]
         self.n1 = (1 << log2_m) // self.n0
         self.local_words = (1 << log2_m) // world
-        self.extra_launches_per_roundtrip = 0  # the tile (un)packing copies are torch's kernels, not ours
+        self.tiled = modulus is None or modulus == 0xFFFFFC6E80000001  # address-mapped kernels: production prime
+        self.chunks = self._pick_chunks(chunks) if self.tiled else 1
+        self.extra_launches_per_roundtrip = 0
         self._tmp = None
 
+    def _pick_chunks(self, want):
+        """Largest power of two <= want (default 4) that the tile shapes allow."""
+        k = want or 4
+        # w = n1 / (G*K) must hold a whole column tile and, for 3-pass plans, whole inner runs of pass 1
+        tile_w = 1 << min(5, max(0, 13 - self.splits[0]))
+        inner1 = 1 << sum(self.splits[2:]) if len(self.splits) > 2 else 1
+        while k > 1 and (self.n1 // (self.world * k) < max(tile_w, inner1) or self.n1 % (self.world * k)):
+            k //= 2
+        return max(k, 1)
+
     def _scratch(self, like):
-        if self._tmp is None or self._tmp[0].device != like.device:
+        if self._tmp is None or self._tmp[0].device != like.device or self._tmp[0].numel() != like.numel():
             self._tmp = (torch.empty_like(like), torch.empty_like(like))
         return self._tmp
 
+    # ---- pipelined path --------------------------------------------------------------------------
     def forward(self, dst, src, stream=0):
         """src: this rank's column block [n0][n1/G]; dst: this rank's row block [n0/G][n1]."""
-        G, n0, n1 = self.world, self.n0, self.n1
+        if not self.tiled:
+            return self._forward_simple(dst, src, stream)
+        K = self.chunks
         send, recv = self._scratch(src)
-        self.plan.shard_forward_cols(send.data_ptr(), src.data_ptr(), stream)
-        # chunk s of `send` = rows [s*n0/G, (s+1)*n0/G) of my columns -> rank s
-        dist.all_to_all_single(recv, send, group=self.group)
-        # recv[s] = my rows x rank s's columns: interleave the G column blocks into whole rows
-        dst.view(n0 // G, G, n1 // G).copy_(recv.view(G, n0 // G, n1 // G).permute(1, 0, 2))
-        self.plan.shard_forward_rows(dst.data_ptr(), dst.data_ptr(), stream)
+        sv, rv = send.view(K, -1), recv.view(K, -1)
+        works = []
+        for c in range(K):
+            self.plan.shard_forward_cols_chunk(send.data_ptr(), src.data_ptr(), c, K, stream)
+            works.append(dist.all_to_all_single(rv[c], sv[c], group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+        self.plan.shard_forward_rows_tiled(dst.data_ptr(), recv.data_ptr(), K, stream)
 
     def inverse(self, dst, src, stream=0):
         """src: row block [n0/G][n1] (bit-reversed order); dst: column block [n0][n1/G]."""
+        if not self.tiled:
+            return self._inverse_simple(dst, src, stream)
+        K = self.chunks
+        send, recv = self._scratch(src)
+        # the row half leaves its result tiled in `send`; `recv` doubles as its scratch
+        self.plan.shard_inverse_rows_tiled(send.data_ptr(), src.data_ptr(), recv.data_ptr(), K, stream)
+        sv, rv = send.view(K, -1), recv.view(K, -1)
+        works = [dist.all_to_all_single(rv[c], sv[c], group=self.group, async_op=True) for c in range(K)]
+        for c in range(K):
+            works[c].wait()
+            self.plan.shard_inverse_cols_chunk(dst.data_ptr(), recv.data_ptr(), c, K, stream)
+
+    # ---- reference path: whole-block exchange + explicit tile interleave (any modulus) -------------
+    def _forward_simple(self, dst, src, stream=0):
+        G, n0, n1 = self.world, self.n0, self.n1
+        send, recv = self._scratch(src)
+        self.plan.shard_forward_cols(send.data_ptr(), src.data_ptr(), stream)
+        dist.all_to_all_single(recv, send, group=self.group)
+        dst.view(n0 // G, G, n1 // G).copy_(recv.view(G, n0 // G, n1 // G).permute(1, 0, 2))
+        self.plan.shard_forward_rows(dst.data_ptr(), dst.data_ptr(), stream)
+
+    def _inverse_simple(self, dst, src, stream=0):
         G, n0, n1 = self.world, self.n0, self.n1
         send, recv = self._scratch(src)
         self.plan.shard_inverse_rows(recv.data_ptr(), src.data_ptr(), stream)
         send.view(G, n0 // G, n1 // G).copy_(recv.view(n0 // G, G, n1 // G).permute(1, 0, 2))
         dist.all_to_all_single(recv, send, group=self.group)
-        # recv[s] = rows of rank s x my columns, already in [n0][n1/G] order
         self.plan.shard_inverse_cols(dst.data_ptr(), recv.data_ptr(), stream)
 
     def close(self):

@@ -60,36 +60,31 @@ static void emu_stages(const PassParams& prm, typename Slot<Cfg::C>::type* sm, c
   (emu_stage_all_threads<F, Cfg, INV, TWIST, Js>(prm, sm, gsrc, gdst, col0, row0), ...);
 }
 
-template <class F, int LOGN, bool COL, bool INV>
+template <class F, int LOGN, bool COL, bool INV, bool MAP>
 static int emu_launch2(const PassParams& prm, unsigned grid) {
   constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
-  typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
+  typedef PassCfg<LOGN, LOGW, C, COL, MAP> Cfg;
   std::vector<typename Slot<C>::type> sm((size_t)Cfg::N * Cfg::NP + 1);
   for (unsigned tile = 0; tile < grid; ++tile) {
     // body of pass_kernel()
-    u64 base;
+    u64 sbase, dbase;
     u32 col0 = 0, row0 = 0;
-    if constexpr (COL) {
-      const u32 o = tile / prm.tiles_per_outer, cb = tile - o * prm.tiles_per_outer;
-      base = (u64)o * prm.outer_stride + (u64)cb * Cfg::W;
-      col0 = prm.twist_col0 + cb * Cfg::W;
-    } else {
-      base = ((u64)tile << (LOGN + LOGW));
-      row0 = tile << LOGW;
-    }
+    tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
     // poison shared memory so that a missing write shows up
     memset(sm.data(), 0xcd, sm.size() * sizeof(sm[0]));
-    emu_stages<F, Cfg, INV, COL>(prm, sm.data(), prm.src + base, prm.dst + base, col0, row0,
+    emu_stages<F, Cfg, INV, COL>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
                               std::make_integer_sequence<int, Cfg::NS>{});
   }
   return 0;
 }
 
+static bool g_map = false;
 template <int LOGN, bool COL, bool INV>
 static int emu_launch(const PassParams& prm, unsigned grid) {
   // same choice as backend_cuda.cu: baked-in modulus for kP0, runtime modulus otherwise
-  if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV>(prm, grid);
-  return emu_launch2<FieldRT, LOGN, COL, INV>(prm, grid);
+  if (g_map) return prm.field.p == kP0 ? emu_launch2<F0, LOGN, COL, INV, true>(prm, grid) : 1;
+  if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV, false>(prm, grid);
+  return emu_launch2<FieldRT, LOGN, COL, INV, false>(prm, grid);
 }
 
 #define EMU_CASE(L)                                                       \
@@ -142,7 +137,8 @@ int pointer_is_device(const void*, int* is_device) {
 }
 const char* last_error() { return g_err.c_str(); }
 
-int launch_pass(int logn, bool col, bool inverse, const PassParams& prm, unsigned grid, void*) {
+int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid, void*) {
+  g_map = map;
   switch (logn) {
     EMU_CASE(1) EMU_CASE(2) EMU_CASE(3) EMU_CASE(4) EMU_CASE(5) EMU_CASE(6) EMU_CASE(7)
     EMU_CASE(8) EMU_CASE(9) EMU_CASE(10) EMU_CASE(11) EMU_CASE(12)

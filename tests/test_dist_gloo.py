@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, log2_m, splits, emu_path, q):
+def _worker(rank, world, port, log2_m, splits, modulus, emu_path, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, os.path.join(ROOT, "sve-ntt_b200"))
@@ -34,14 +34,15 @@ def _worker(rank, world, port, log2_m, splits, emu_path, q):
         lib = pkg.Library(emu_path)
         orc = oracle_lib.Oracle()
         m = 1 << log2_m
-        a = orc.fill_xorshift(m, SEED, P0)
-        sh = dist_ntt.ShardedNTT(lib, log2_m, world, rank, splits=splits)
+        N, g = (P0, G0) if modulus is None else modulus
+        a = orc.fill_xorshift(m, SEED, N)
+        sh = dist_ntt.ShardedNTT(lib, log2_m, world, rank, splits=splits, modulus=N, generator=g)
         n0, n1 = sh.n0, sh.n1
         block = np.ascontiguousarray(a.reshape(n0, n1)[:, rank * n1 // world:(rank + 1) * n1 // world])
         src = torch.from_numpy(block.view(np.int64).reshape(-1).copy())
         dst = torch.empty_like(src)
         sh.forward(dst, src)
-        want = orc.ntt_forward(a, P0, G0)[rank * m // world:(rank + 1) * m // world]
+        want = orc.ntt_forward(a, N, g)[rank * m // world:(rank + 1) * m // world]
         ok_f = bool(np.array_equal(dst.numpy().view(np.uint64), want))
         back = torch.empty_like(src)
         sh.inverse(back, dst)
@@ -51,12 +52,15 @@ def _worker(rank, world, port, log2_m, splits, emu_path, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,log2_m,splits", [(2, 14, [7, 7]), (4, 16, [6, 5, 5]), (2, 15, None)])
-def test_sharded_transform_over_gloo(emu, world, log2_m, splits):
+@pytest.mark.parametrize("world,log2_m,splits,modulus", [
+    (2, 14, [7, 7], None), (4, 16, [6, 5, 5], None), (2, 15, None, None), (4, 18, [7, 11], None),
+    (2, 14, [7, 7], (0x3A00000000000001, 3)),  # other moduli take the whole-block path
+])
+def test_sharded_transform_over_gloo(emu, world, log2_m, splits, modulus):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, log2_m, splits, emu.path, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, log2_m, splits, modulus, emu.path, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

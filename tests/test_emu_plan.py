@@ -259,3 +259,51 @@ def test_fused_forward_multiply(emu, oracle, L, splits, N, g):
     assert np.array_equal(fused, want)
     plan.inverse(fused.ctypes.data, fused.ctypes.data)
     assert np.array_equal(fused, oracle.ntt_inverse(want, N, g))
+
+
+@pytest.mark.parametrize("L,splits,G,K", [(14, [7, 7], 2, 1), (14, [7, 7], 2, 2), (16, [6, 5, 5], 4, 1), (18, [6, 6, 6], 2, 2),
+                                         (18, [7, 11], 4, 4), (17, [8, 4, 5], 2, 2)])
+def test_sharded_tiled_variants(emu, oracle, L, splits, G, K):
+    """Chunked column passes + tiled row half (no separate pack/unpack pass): numpy plays the
+    all-to-all, chunk by chunk; result == oracle, and the inverse returns the column blocks."""
+    m = 1 << L
+    n0 = 1 << splits[0]
+    n1 = m // n0
+    w = n1 // (G * K)
+    a = oracle.fill_xorshift(m, SEED + 11, P0)
+    want = oracle.ntt_forward(a, P0, G0)
+    A = a.reshape(n0, n1)
+    plans = [emu.plan(L, splits=splits, shard_count=G, shard_rank=r) for r in range(G)]
+    blocks = [np.ascontiguousarray(A[:, r * n1 // G:(r + 1) * n1 // G]).reshape(-1) for r in range(G)]
+    send = [np.full(m // G, 0xDEAD, np.uint64) for _ in range(G)]
+    for r in range(G):
+        for c in range(K):
+            plans[r].shard_forward_cols_chunk(send[r].ctypes.data, blocks[r].ctypes.data, c, K)
+    # all-to-all per chunk: message (chunk c, dest s) of rank r = send[r][c][s]
+    recv = [np.empty(m // G, np.uint64) for _ in range(G)]
+    msg = (n0 // G) * w
+    for r in range(G):
+        sv = send[r].reshape(K, G, msg)
+        for s in range(G):
+            recv[s].reshape(K, G, msg)[:, r, :] = sv[:, s, :]
+    outs = []
+    for r in range(G):
+        dst = np.empty(m // G, np.uint64)
+        plans[r].shard_forward_rows_tiled(dst.ctypes.data, recv[r].ctypes.data, K)
+        outs.append(dst)
+    assert np.array_equal(np.concatenate(outs), want), (L, splits, G, K)
+    # inverse
+    tiles = [np.empty(m // G, np.uint64) for _ in range(G)]
+    work = [np.empty(m // G, np.uint64) for _ in range(G)]
+    for r in range(G):
+        plans[r].shard_inverse_rows_tiled(tiles[r].ctypes.data, outs[r].ctypes.data, work[r].ctypes.data, K)
+    back_tiles = [np.empty(m // G, np.uint64) for _ in range(G)]
+    for r in range(G):
+        tv = tiles[r].reshape(K, G, msg)
+        for s in range(G):
+            back_tiles[s].reshape(K, G, msg)[:, r, :] = tv[:, s, :]
+    for r in range(G):
+        got = np.empty(m // G, np.uint64)
+        for c in range(K):
+            plans[r].shard_inverse_cols_chunk(got.ctypes.data, back_tiles[r].ctypes.data, c, K)
+        assert np.array_equal(got, blocks[r]), (L, splits, G, K, r)
