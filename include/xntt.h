@@ -129,6 +129,21 @@ int xntt_shard_inverse_rows_tiled(const xntt_plan* plan, uint64_t* tiles, const 
 int xntt_shard_inverse_cols_chunk(const xntt_plan* plan, uint64_t* dst, const uint64_t* tiles, uint32_t chunk,
                                   uint32_t nchunks, void* stream);
 
+/* Fused compute + exchange over peer memory (NVLink / NVSwitch): the pass next to the all-to-all
+ * stores its output directly into every rank's buffer, so no collective is issued at all.
+ * peers[s] = device address, valid on THIS GPU, of rank s's exchange buffer (m / shard_count words,
+ * e.g. torch symmetric memory or cudaIpc mappings), s = 0 .. shard_count-1 (at most 8).
+ *   forward_cols_peer : column pass + twiddle; rank s receives my rows of its row block at
+ *                       peers[s] + rank * (n0/G) * (n1/G), i.e. the tiled layout with one chunk -
+ *                       after a cross-rank barrier, xntt_shard_forward_rows_tiled(dst, own buffer, 1)
+ *   inverse_rows_peer : row half of the inverse; rank s receives its columns of my rows in chunk
+ *                       layout - after a barrier, xntt_shard_inverse_cols_chunk(dst, own buffer, 0, 1)
+ * The caller orders the barriers (all writers done before anyone reads; readers done before the
+ * buffer is written again - two alternating buffers make the second barrier unnecessary). */
+int xntt_shard_forward_cols_peer(const xntt_plan* plan, uint64_t* const* peers, const uint64_t* src, void* stream);
+int xntt_shard_inverse_rows_peer(const xntt_plan* plan, uint64_t* const* peers, const uint64_t* src, uint64_t* work,
+                                 void* stream);
+
 /* PAdic64 element-wise helpers on device buffers (count words each):
  *   to_montgomery      : dst[i] = src[i] * 2^64 mod p     (modmul/sve/p-adic-64.hpp:19-22)
  *   from_montgomery    : dst[i] = src[i] * 2^-64 mod p    (p-adic-64.hpp:24-38, canonical result)

@@ -67,6 +67,8 @@ SYMBOLS = {
     "xntt_shard_forward_rows_tiled": (C.c_int, [_P, _U64P, _U64P, C.c_uint32, _P]),
     "xntt_shard_inverse_rows_tiled": (C.c_int, [_P, _U64P, _U64P, _U64P, C.c_uint32, _P]),
     "xntt_shard_inverse_cols_chunk": (C.c_int, [_P, _U64P, _U64P, C.c_uint32, C.c_uint32, _P]),
+    "xntt_shard_forward_cols_peer": (C.c_int, [_P, C.POINTER(C.c_void_p), _U64P, _P]),
+    "xntt_shard_inverse_rows_peer": (C.c_int, [_P, C.POINTER(C.c_void_p), _U64P, _U64P, _P]),
     "xntt_to_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
     "xntt_from_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
     "xntt_multiply_normalize": (C.c_int, [_P, _U64P, _U64P, _U64P, C.c_size_t, _P]),
@@ -213,6 +215,14 @@ class Plan:
 
     def shard_inverse_cols_chunk(self, dst, tiles, chunk, nchunks, stream=0):
         self._call("xntt_shard_inverse_cols_chunk", dst, tiles, chunk, nchunks, stream)
+
+    def shard_forward_cols_peer(self, peers, src, stream=0):
+        arr = (C.c_void_p * len(peers))(*peers)
+        self._call("xntt_shard_forward_cols_peer", arr, src, stream)
+
+    def shard_inverse_rows_peer(self, peers, src, work, stream=0):
+        arr = (C.c_void_p * len(peers))(*peers)
+        self._call("xntt_shard_inverse_rows_peer", arr, src, work, stream)
 
     def to_montgomery(self, dst, src, count, stream=0):
         self._call("xntt_to_montgomery", dst, src, count, stream)

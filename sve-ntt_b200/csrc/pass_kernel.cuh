@@ -161,6 +161,29 @@ __device__ __forceinline__ void gmem_load(const PassParams& prm, const u64* base
 template <class Cfg, int R>
 __device__ __forceinline__ void gmem_store(const PassParams& prm, u64* base, u32 row0, int k0, int logs, int p,
                                            const u64 (&x)[R][Cfg::C]) {
+  if constexpr (Cfg::MAP) {
+    if (prm.peer_bits != 0) {
+      // fused exchange: the owner of output index k is rank k >> peer_bits; all ranks' buffers share one
+      // layout, so the tile offset (base - prm.dst) carries over
+      const u64 tile_ofs = (u64)(base - prm.dst);
+      const int kmask = (1 << prm.peer_bits) - 1;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int k = k0 + (r << logs);
+        u64* pb = prm.peer[(u32)k >> prm.peer_bits] + tile_ofs;
+        if constexpr (Cfg::COL && Cfg::C == 2) {
+          *reinterpret_cast<ulonglong2*>(pb + gofs<Cfg>(prm, prm.dmap, k & kmask, p, 0)) =
+              make_ulonglong2(x[r][0], x[r][1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < Cfg::C; ++c)
+            if (Cfg::COL || row0 + (u32)(p * Cfg::C + c) < prm.rows)
+              pb[gofs<Cfg>(prm, prm.dmap, k & kmask, p, c)] = x[r][c];
+        }
+      }
+      return;
+    }
+  }
   if constexpr (Cfg::COL) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {

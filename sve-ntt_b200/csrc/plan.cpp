@@ -259,7 +259,8 @@ int tiled_map(const xntt_plan* pl, u32 nchunks, StrideMap& out) {
 }
 
 int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* src, const StrideMap& smap,
-                    const StrideMap& dmap, u64 units, u32 tiles_per_outer, u32 twist_col0, void* st) {
+                    const StrideMap& dmap, u64 units, u32 tiles_per_outer, u32 twist_col0, void* st,
+                    u64* const* peers = nullptr, u32 peer_bits = 0, u64 peer_offset = 0) {
   const PassDesc& ps = pl->passes[i];
   PassParams prm{};
   prm.src = src;
@@ -269,6 +270,11 @@ int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const
   prm.field = pl->field;
   prm.smap = smap;
   prm.dmap = dmap;
+  if (peers) {
+    for (u32 s = 0; s < pl->shard_count; ++s) prm.peer[s] = peers[s] + peer_offset;
+    prm.peer_bits = peer_bits;
+    prm.dst = peers[pl->shard_rank] + peer_offset;  // tile offsets are taken relative to prm.dst
+  }
   const int logw = tile_logw(ps.logn);
   unsigned grid;
   if (ps.col) {
@@ -600,6 +606,66 @@ int xntt_shard_inverse_rows_tiled(const xntt_plan* pl, uint64_t* tiles, const ui
   const u64 rows0 = (1ull << pl->passes[0].logn) / pl->shard_count;
   const u32 tpo = p1.col ? (u32)((1ull << p1.log_inner) >> tile_logw(p1.logn)) : 0u;
   return run_pass_mapped(pl, 1, true, (u64*)tiles, cur, natural_map(pl, p1), tm, rows0, tpo, 0, stream);
+}
+
+// Fused exchange: the pass next to the all-to-all stores straight into every rank's tiled buffer.
+// peers[s] = base of rank s's buffer of m / G words, laid out [G (source rank)][n0/G][n1/G].
+int xntt_shard_forward_cols_peer(const xntt_plan* pl, uint64_t* const* peers, const uint64_t* src, void* stream) {
+  if (!pl || !peers || !src || pl->shard_count < 2 || pl->shard_count > 8) return XNTT_ERR_STATE;
+  if (!pl->fwd) return XNTT_ERR_STATE;
+  if (pl->batch != 1) return XNTT_ERR_INVALID;
+  const PassDesc& p0 = pl->passes[0];
+  const u64 G = pl->shard_count, n0 = 1ull << p0.logn, n1 = (1ull << pl->log2_m) / n0, block = n1 / G;
+  if (n0 / G < 1) return XNTT_ERR_INVALID;
+  DeviceGuard g(pl->device);
+  if (!g.ok) return be_fail(1);
+  StrideMap full{}, tile{};
+  full.b1 = full.b2 = tile.b1 = tile.b2 = 31;
+  full.s0 = block;
+  full.outer = n0 * block;
+  tile.s0 = block;  // row rho of the (n0/G) x (n1/G) tile
+  tile.outer = 0;
+  const u32 tpo = (u32)(block >> tile_logw(p0.logn));
+  const u32 col0 = (u32)(block * pl->shard_rank);
+  // my tile inside every destination buffer starts at rank * (n0/G) * (n1/G)
+  return run_pass_mapped(pl, 0, false, nullptr, (const u64*)src, full, tile, 1, tpo, col0, stream, (u64* const*)peers,
+                         (u32)log2u(n0 / G), (n0 / G) * block * pl->shard_rank);
+}
+int xntt_shard_inverse_rows_peer(const xntt_plan* pl, uint64_t* const* peers, const uint64_t* src, uint64_t* work,
+                                 void* stream) {
+  if (!pl || !peers || !src || pl->shard_count < 2 || pl->shard_count > 8) return XNTT_ERR_STATE;
+  if (!pl->inv) return XNTT_ERR_STATE;
+  if (pl->batch != 1) return XNTT_ERR_INVALID;
+  DeviceGuard g(pl->device);
+  if (!g.ok) return be_fail(1);
+  const u64* cur = (const u64*)src;
+  int rc;
+  if (pl->passes.size() > 2) {
+    if (!work) return XNTT_ERR_INVALID;
+    rc = run_range(pl, true, 2, pl->passes.size(), (u64*)work, cur, stream, true);
+    if (rc != XNTT_OK) return rc;
+    cur = (const u64*)work;
+  }
+  const PassDesc& p1 = pl->passes[1];
+  const u64 G = pl->shard_count, n0 = 1ull << pl->passes[0].logn, n1 = (1ull << pl->log2_m) / n0, block = n1 / G;
+  const u64 rows0 = n0 / G;
+  // destination (rank s): chunk layout [n0][n1/G], my rows start at rank * (n0/G); element (rho, c')
+  StrideMap dm{};
+  dm.b1 = dm.b2 = 31;
+  dm.outer = block;  // next local row rho
+  u32 peer_bits;
+  if (p1.col) {
+    const u64 n1b = 1ull << p1.log_inner;
+    if (block % n1b) return XNTT_ERR_UNSUPPORTED;
+    dm.s0 = n1b;
+    peer_bits = (u32)log2u(block / n1b);
+  } else {
+    dm.s0 = 1;
+    peer_bits = (u32)log2u(block);
+  }
+  const u32 tpo = p1.col ? (u32)((1ull << p1.log_inner) >> tile_logw(p1.logn)) : 0u;
+  return run_pass_mapped(pl, 1, true, nullptr, cur, natural_map(pl, p1), dm, rows0, tpo, 0, stream, (u64* const*)peers,
+                         peer_bits, rows0 * block * pl->shard_rank);
 }
 
 int xntt_forward_host(const xntt_plan* pl, uint64_t* dst, const uint64_t* src) {

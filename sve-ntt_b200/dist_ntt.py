@@ -10,6 +10,14 @@ Layout, m = n0 * n1 viewed as an n0 x n1 row-major matrix, G ranks:
 forward  = column passes + twiddle (local) -> all-to-all of (n0/G x n1/G) tiles -> row passes (local)
 inverse  = row passes -> all-to-all -> column passes; back in the column-block layout.
 
+Exchange, fastest first:
+  "peer"      the pass next to the exchange stores its output directly into every rank's buffer over
+              NVLink (torch symmetric memory provides the peer mappings and the stream-ordered
+              barrier): compute and all-to-all are ONE kernel, no collective is issued
+              (xntt_shard_forward_cols_peer / xntt_shard_inverse_rows_peer);
+  "pipelined" NCCL all_to_all_single per column chunk, overlapped with the next chunk's compute;
+  "simple"    whole-block all-to-all + explicit tile interleave (any modulus).
+
 Pipelining: the column block is processed in K column chunks; chunk c's all-to-all (async, NCCL's
 own stream) runs while chunk c+1 computes, and the row half reads the received tiles in place
 (xntt_shard_*_tiled), so there is no separate pack/unpack pass over memory.
@@ -23,7 +31,7 @@ import torch.distributed as dist
 
 class ShardedNTT:
     def __init__(self, library, log2_m, world, rank, device=-1, splits=None, group=None, inverse_factor=None,
-                 chunks=None, modulus=None, generator=None):
+                 chunks=None, modulus=None, generator=None, mode=None):
         self.world, self.rank, self.group = world, rank, group
         kw = {}
         if modulus is not None:
@@ -38,6 +46,36 @@ class ShardedNTT:
         self.chunks = self._pick_chunks(chunks) if self.tiled else 1
         self.extra_launches_per_roundtrip = 0
         self._tmp = None
+        self.mode = mode or ("peer" if self.tiled else "simple")
+        if not self.tiled:
+            self.mode = "simple"
+        self._peer = None  # (buffers, handles, parity)
+        if self.mode == "peer":
+            try:
+                self._setup_peer(device)
+            except Exception as exc:  # no P2P / symmetric memory here (e.g. gloo on CPU): NCCL path
+                self._peer_error = repr(exc)
+                self.mode = "pipelined"
+
+    def _setup_peer(self, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        if not torch.cuda.is_available() or dist.get_backend(self.group) != "nccl" or self.world > 8:
+            raise RuntimeError("peer mode needs CUDA + NCCL and at most 8 ranks")
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None or device < 0 else device)
+        group = self.group if self.group is not None else dist.group.WORLD
+        bufs, hdls = [], []
+        for _ in range(2):  # two alternating exchange buffers: one barrier per transform suffices
+            t = symm_mem.empty(self.local_words, dtype=torch.int64, device=dev)
+            h = symm_mem.rendezvous(t, group)
+            bufs.append(t)
+            hdls.append(h)
+        self._peer = {"bufs": bufs, "hdls": hdls, "parity": 0,
+                      "ptrs": [[int(p) for p in h.buffer_ptrs] for h in hdls]}
+
+    def _next_peer(self):
+        i = self._peer["parity"]
+        self._peer["parity"] ^= 1
+        return self._peer["bufs"][i], self._peer["hdls"][i], self._peer["ptrs"][i]
 
     def _pick_chunks(self, want):
         """Largest power of two <= want (default 4) that the tile shapes allow."""
@@ -57,8 +95,14 @@ class ShardedNTT:
     # ---- pipelined path --------------------------------------------------------------------------
     def forward(self, dst, src, stream=0):
         """src: this rank's column block [n0][n1/G]; dst: this rank's row block [n0/G][n1]."""
-        if not self.tiled:
+        if self.mode == "simple":
             return self._forward_simple(dst, src, stream)
+        if self.mode == "peer":
+            buf, hdl, ptrs = self._next_peer()
+            self.plan.shard_forward_cols_peer(ptrs, src.data_ptr(), stream)
+            hdl.barrier(channel=0)  # every rank's tiles have landed in everybody's buffer
+            self.plan.shard_forward_rows_tiled(dst.data_ptr(), buf.data_ptr(), 1, stream)
+            return
         K = self.chunks
         send, recv = self._scratch(src)
         sv, rv = send.view(K, -1), recv.view(K, -1)
@@ -72,8 +116,15 @@ class ShardedNTT:
 
     def inverse(self, dst, src, stream=0):
         """src: row block [n0/G][n1] (bit-reversed order); dst: column block [n0][n1/G]."""
-        if not self.tiled:
+        if self.mode == "simple":
             return self._inverse_simple(dst, src, stream)
+        if self.mode == "peer":
+            buf, hdl, ptrs = self._next_peer()
+            work = self._scratch(src)[0]
+            self.plan.shard_inverse_rows_peer(ptrs, src.data_ptr(), work.data_ptr(), stream)
+            hdl.barrier(channel=0)
+            self.plan.shard_inverse_cols_chunk(dst.data_ptr(), buf.data_ptr(), 0, 1, stream)
+            return
         K = self.chunks
         send, recv = self._scratch(src)
         # the row half leaves its result tiled in `send`; `recv` doubles as its scratch

@@ -307,3 +307,36 @@ def test_sharded_tiled_variants(emu, oracle, L, splits, G, K):
         for c in range(K):
             plans[r].shard_inverse_cols_chunk(got.ctypes.data, back_tiles[r].ctypes.data, c, K)
         assert np.array_equal(got, blocks[r]), (L, splits, G, K, r)
+
+
+@pytest.mark.parametrize("L,splits,G", [(14, [7, 7], 2), (16, [6, 5, 5], 4), (18, [7, 11], 8), (17, [8, 4, 5], 2)])
+def test_sharded_peer_store_variants(emu, oracle, L, splits, G):
+    """Fused exchange: the pass next to the all-to-all stores straight into every rank's buffer
+    (peer pointers).  All ranks live in this process, so 'peer memory' is just the other arrays."""
+    m = 1 << L
+    n0 = 1 << splits[0]
+    n1 = m // n0
+    a = oracle.fill_xorshift(m, SEED + 12, P0)
+    want = oracle.ntt_forward(a, P0, G0)
+    A = a.reshape(n0, n1)
+    plans = [emu.plan(L, splits=splits, shard_count=G, shard_rank=r) for r in range(G)]
+    blocks = [np.ascontiguousarray(A[:, r * n1 // G:(r + 1) * n1 // G]).reshape(-1) for r in range(G)]
+    bufs = [np.full(m // G, 0xDEAD, np.uint64) for _ in range(G)]
+    peers = [b.ctypes.data for b in bufs]
+    for r in range(G):
+        plans[r].shard_forward_cols_peer(peers, blocks[r].ctypes.data)
+    outs = []
+    for r in range(G):
+        dst = np.empty(m // G, np.uint64)
+        plans[r].shard_forward_rows_tiled(dst.ctypes.data, bufs[r].ctypes.data, 1)
+        outs.append(dst)
+    assert np.array_equal(np.concatenate(outs), want), (L, splits, G)
+    bufs2 = [np.full(m // G, 0xBEEF, np.uint64) for _ in range(G)]
+    peers2 = [b.ctypes.data for b in bufs2]
+    work = np.empty(m // G, np.uint64)
+    for r in range(G):
+        plans[r].shard_inverse_rows_peer(peers2, outs[r].ctypes.data, work.ctypes.data)
+    for r in range(G):
+        got = np.empty(m // G, np.uint64)
+        plans[r].shard_inverse_cols_chunk(got.ctypes.data, bufs2[r].ctypes.data, 0, 1)
+        assert np.array_equal(got, blocks[r]), (L, splits, G, r)

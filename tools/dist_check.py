@@ -26,7 +26,9 @@ sizes = [int(a) for a in sys.argv[1:]] or [20, 24, 26]
 out = []
 for L in sizes:
     m = 1 << L
-    sh = dist_ntt.ShardedNTT(lib, L, world, rank, device=local)
+    sh = dist_ntt.ShardedNTT(lib, L, world, rank, device=local, mode=os.environ.get("XNTT_DIST_MODE"))
+    if rank == 0:
+        print("mode", sh.mode, getattr(sh, "_peer_error", ""), flush=True)
     n0, n1 = sh.n0, sh.n1
     # every rank builds the same full input, keeps its column block
     gen = torch.Generator(device=dev)
@@ -75,7 +77,7 @@ for L in sizes:
     flags = torch.tensor([int(bool(ok_f) or ok_f is None), int(ok_i)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
-        rec = {"log2_m": L, "world": world, "splits": sh.splits, "forward_equal_single_gpu": bool(flags[0].item()) if check else None,
+        rec = {"log2_m": L, "world": world, "mode": sh.mode, "splits": sh.splits, "forward_equal_single_gpu": bool(flags[0].item()) if check else None,
                "roundtrip": bool(flags[1].item()), "fwd_ms": float(tf.item()), "inv_ms": float(ti.item()),
                "fwd_gelem_s": m / float(tf.item()) / 1e6, "inv_gelem_s": m / float(ti.item()) / 1e6}
         out.append(rec)
