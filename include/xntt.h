@@ -156,6 +156,12 @@ int xntt_from_montgomery(const xntt_plan* plan, uint64_t* dst, const uint64_t* s
 int xntt_multiply_normalize(const xntt_plan* plan, uint64_t* dst, const uint64_t* a, const uint64_t* b_mont,
                             size_t count, void* stream);
 
+/* Transpose*::transpose(dst, src, src_rows, src_cols, ld_dst, ld_src)
+ * (every class under include/sventt/transposition/sve/): dst[ld_dst * c + r] = src[ld_src * r + c] on device buffers;
+ * dst == src with rows == cols and ld_dst == ld_src is the in-place square form transpose(dst, dim). */
+int xntt_transpose(uint64_t* dst, const uint64_t* src, uint64_t rows, uint64_t cols, uint64_t ld_dst, uint64_t ld_src,
+                   void* stream);
+
 /* Device-resident PageMemory twin (include/sventt/vector.hpp:61-168): pinned host memory for the
  * host entry points / device memory for the device ones. */
 int xntt_alloc_device(void** ptr, size_t bytes, int device);

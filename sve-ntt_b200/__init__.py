@@ -72,6 +72,7 @@ SYMBOLS = {
     "xntt_to_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
     "xntt_from_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
     "xntt_multiply_normalize": (C.c_int, [_P, _U64P, _U64P, _U64P, C.c_size_t, _P]),
+    "xntt_transpose": (C.c_int, [_U64P, _U64P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
     "xntt_alloc_device": (C.c_int, [C.POINTER(_P), C.c_size_t, C.c_int]),
     "xntt_free_device": (C.c_int, [_P]),
     "xntt_alloc_pinned": (C.c_int, [C.POINTER(_P), C.c_size_t]),
@@ -119,6 +120,10 @@ class Library:
 
     def plan(self, log2_m, **kw):
         return Plan(self, log2_m, **kw)
+
+    def transpose(self, dst, src, rows, cols, ld_dst=None, ld_src=None, stream=0):
+        self.check(self.lib.xntt_transpose(dst, src, rows, cols, rows if ld_dst is None else ld_dst,
+                                           cols if ld_src is None else ld_src, stream), "xntt_transpose")
 
     def microbench(self, kind, iters):
         g, ms = C.c_double(), C.c_double()

@@ -32,6 +32,9 @@ int launch_gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int lo
 int launch_to_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, u64 r2, void* stream);
 int launch_from_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, void* stream);
 int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, size_t n, void* stream);
+// dst[ld_dst * c + r] = src[ld_src * r + c]; dst == src with rows == cols and equal leading dimensions
+// is the in-place square form
+int launch_transpose(u64* dst, const u64* src, u64 rows, u64 cols, u64 ld_dst, u64 ld_src, void* stream);
 int microbench(int kind, int iters, double* gops, double* ms);
 
 }  // namespace be

@@ -9,6 +9,7 @@
 #include "backend.h"
 #include "dispatch.cuh"
 #include "misc_kernels.cuh"
+#include "transpose_kernel.cuh"
 
 namespace xntt {
 
@@ -271,6 +272,28 @@ int launch_from_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, 
 }
 int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, size_t n, void* st) {
   XNTT_WITH_FIELD(fc, (mulnorm_kernel<F><<<ew_grid(n), 256, 0, (cudaStream_t)st>>>(f, dst, a, b, n)));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int launch_transpose(u64* dst, const u64* src, u64 rows, u64 cols, u64 ld_dst, u64 ld_src, void* stream) {
+  TransposeParams p{dst, src, rows, cols, ld_dst, ld_src, (u32)((cols + kTrTile - 1) / kTrTile)};
+  const u64 tiles_r = (rows + kTrTile - 1) / kTrTile;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(kTrSmemWords * sizeof(u64))));
+    CU(cudaFuncSetAttribute(transpose_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(2 * kTrSmemWords * sizeof(u64))));
+    attr_done = true;
+  }
+  if (dst == src) {
+    const u64 t = p.tiles_c, pairs = t * (t + 1) / 2;
+    transpose_inplace_kernel<<<(unsigned)pairs, kTrThreads, 2 * kTrSmemWords * sizeof(u64), (cudaStream_t)stream>>>(p);
+  } else {
+    transpose_kernel<<<(unsigned)(tiles_r * p.tiles_c), kTrThreads, kTrSmemWords * sizeof(u64),
+                       (cudaStream_t)stream>>>(p);
+  }
   CU(cudaGetLastError());
   return 0;
 }

@@ -732,6 +732,17 @@ int xntt_stream_synchronize(void* st) {
   return XNTT_OK;
 }
 
+int xntt_transpose(uint64_t* dst, const uint64_t* src, uint64_t rows, uint64_t cols, uint64_t ld_dst, uint64_t ld_src,
+                   void* stream) {
+  if (!dst || !src) return XNTT_ERR_INVALID;
+  if (rows == 0 || cols == 0) return XNTT_OK;
+  if (ld_src < cols || ld_dst < rows) return XNTT_ERR_INVALID;
+  if (dst == src && (rows != cols || ld_dst != ld_src)) return XNTT_ERR_INVALID;  // in place: square only
+  if (rows > 0xffffffffull || cols > 0xffffffffull) return XNTT_ERR_INVALID;
+  BE(be::launch_transpose((u64*)dst, (const u64*)src, rows, cols, ld_dst, ld_src, stream));
+  return XNTT_OK;
+}
+
 int xntt_pointer_is_device(const void* ptr) {
   int k = 0;
   BE(be::pointer_is_device(ptr, &k));

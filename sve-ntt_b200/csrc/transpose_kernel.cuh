@@ -1,0 +1,80 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// Stand-alone tiled transposition with the contract of the reference's 17 Transpose* classes
+// (include/sventt/transposition/sve/*.hpp, e.g. in-register.hpp:16-109 and
+// in-register-explicit-blocking-row-first.hpp:28-124):
+//     out of place : dst[ld_dst * c + r] = src[ld_src * r + c]   for r < rows, c < cols
+//     in place     : square, dst[ld * c + r] <-> dst[ld * r + c]
+// One CTA moves a 64 x 64 tile of u64 through padded shared memory: coalesced 512-byte row segments on
+// both the load and the store side.  (Inside the transforms no transposition runs at all - the column
+// pass reads its strided tile directly; this kernel exists for callers that use the classes on their own,
+// as tests/bench-transpose.cpp does.)
+#pragma once
+#include "params.h"
+
+namespace xntt {
+
+constexpr int kTrTile = 64;
+constexpr int kTrPad = 1;
+constexpr int kTrThreads = 256;
+constexpr size_t kTrSmemWords = (size_t)kTrTile * (kTrTile + kTrPad);
+
+struct TransposeParams {
+  u64* dst;
+  const u64* src;
+  u64 rows, cols, ld_dst, ld_src;
+  u32 tiles_c;  // tiles along the column direction of src
+};
+
+// phase 1: src tile (r0.., c0..) -> smem[r][c]
+__device__ __forceinline__ void tr_load(const u64* __restrict__ src, u64 ld, u64 rows, u64 cols, u64 r0, u64 c0,
+                                        u64* sm, int tid) {
+  const int tx = tid & (kTrTile - 1), ty = tid >> 6;  // 64 columns x 4 rows per sweep
+#pragma unroll 4
+  for (int i = ty; i < kTrTile; i += kTrThreads / kTrTile) {
+    const u64 r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) sm[i * (kTrTile + kTrPad) + tx] = src[ld * r + c];
+  }
+}
+// phase 2: smem[r][c] -> dst tile at (c0.., r0..), i.e. transposed
+__device__ __forceinline__ void tr_store(u64* __restrict__ dst, u64 ld, u64 rows, u64 cols, u64 r0, u64 c0,
+                                         const u64* sm, int tid) {
+  const int tx = tid & (kTrTile - 1), ty = tid >> 6;
+#pragma unroll 4
+  for (int i = ty; i < kTrTile; i += kTrThreads / kTrTile) {
+    const u64 c = c0 + i, r = r0 + tx;  // dst row = src column
+    if (r < rows && c < cols) dst[ld * c + r] = sm[tx * (kTrTile + kTrPad) + i];
+  }
+}
+
+#if !defined(XNTT_HOST_EMU)
+__global__ void __launch_bounds__(kTrThreads) transpose_kernel(const __grid_constant__ TransposeParams p) {
+  extern __shared__ __align__(16) unsigned char tr_smem_raw[];
+  u64* sm = reinterpret_cast<u64*>(tr_smem_raw);
+  const u64 tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
+  const u64 r0 = tr * kTrTile, c0 = tc * kTrTile;
+  tr_load(p.src, p.ld_src, p.rows, p.cols, r0, c0, sm, threadIdx.x);
+  __syncthreads();
+  tr_store(p.dst, p.ld_dst, p.rows, p.cols, r0, c0, sm, threadIdx.x);
+}
+
+// in place, square: CTA (i, j), i <= j, swaps tile (i, j) with tile (j, i)
+__global__ void __launch_bounds__(kTrThreads) transpose_inplace_kernel(const __grid_constant__ TransposeParams p) {
+  extern __shared__ __align__(16) unsigned char tr_smem_raw[];
+  u64* sa = reinterpret_cast<u64*>(tr_smem_raw);
+  u64* sb = sa + kTrSmemWords;
+  // unrank the upper-triangular pair index
+  const u32 t = p.tiles_c;
+  u32 i = 0, rem = blockIdx.x;
+  while (rem >= t - i) rem -= t - i, ++i;
+  const u32 j = i + rem;
+  const u64 r0 = (u64)i * kTrTile, c0 = (u64)j * kTrTile;
+  tr_load(p.dst, p.ld_dst, p.rows, p.cols, r0, c0, sa, threadIdx.x);
+  if (i != j) tr_load(p.dst, p.ld_dst, p.rows, p.cols, c0, r0, sb, threadIdx.x);
+  __syncthreads();
+  tr_store(p.dst, p.ld_dst, p.rows, p.cols, r0, c0, sa, threadIdx.x);
+  if (i != j) tr_store(p.dst, p.ld_dst, p.rows, p.cols, c0, r0, sb, threadIdx.x);
+}
+#endif
+
+}  // namespace xntt

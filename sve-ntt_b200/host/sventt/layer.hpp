@@ -15,6 +15,9 @@
 #define XNTT_SVENTT_LAYER_HPP
 
 #include <cstdint>
+#include <stdexcept>
+
+#include "xntt.h"
 
 namespace sventt {
 
@@ -84,10 +87,23 @@ template <class modmul_type, std::uint64_t m, class inner_kernel_type, std::uint
 using BlockedGenericSVELayer = BlockedGenericLayer<modmul_type, m, inner_kernel_type, block_padding_elements,
                                                    twiddle_unroll_count, block_rows, transposition_type>;
 
-// Transposition policy classes of include/sventt/transposition/sve/*.hpp: on the B200 the tiled
-// transposition is what the strided tile load/store of the column pass does, so these are tags.
+// Transposition classes of include/sventt/transposition/sve/ (17 variants of one contract,
+// transpose(dst, src, src_rows, src_cols, ld_dst, ld_src) => dst[ld_dst * c + r] = src[ld_src * r + c], and
+// the in-place square transpose(dst, dim)).  As layer arguments they are tags - inside a transform the
+// column pass reads its strided tile directly - and called on their own they run libxntt's tiled
+// transposition kernel on DEVICE buffers (block-shape parameters are accepted and ignored).
 template <std::uint64_t... params>
-struct TransposeTag {};
+struct TransposeTag {
+  static void transpose(std::uint64_t* dst, const std::uint64_t* src, std::uint64_t src_rows, std::uint64_t src_cols,
+                        std::uint64_t ld_dst, std::uint64_t ld_src, void* stream = nullptr) {
+    const int status = xntt_transpose(dst, src, src_rows, src_cols, ld_dst, ld_src, stream);
+    if (status == XNTT_ERR_INVALID) throw std::invalid_argument{"transpose: invalid shape"};
+    if (status != XNTT_OK) throw std::runtime_error{xntt_last_cuda_error()};
+  }
+  static void transpose(std::uint64_t* dst, std::uint64_t dim, void* stream = nullptr) {
+    transpose(dst, dst, dim, dim, dim, dim, stream);
+  }
+};
 #define XNTT_TRANSPOSE_TAG(NAME)    \
   template <std::uint64_t... params> \
   using NAME = TransposeTag<params...>;
@@ -99,6 +115,10 @@ XNTT_TRANSPOSE_TAG(TransposeSVEInRegisterExplicitBlockingRowFirst)
 XNTT_TRANSPOSE_TAG(TransposeParallelSVEInRegisterExplicitBlockingRowFirst)
 XNTT_TRANSPOSE_TAG(TransposeSVEInRegisterFullBlockingRowFirst)
 XNTT_TRANSPOSE_TAG(TransposeParallelSVEInRegisterFullBlockingRowFirst)
+XNTT_TRANSPOSE_TAG(TransposeSVEGatherImmediateIndexRowFirst)
+XNTT_TRANSPOSE_TAG(TransposeSVEGatherImmediateIndexColumnFirst)
+XNTT_TRANSPOSE_TAG(TransposeSVEGatherVectorIndexRowFirst)
+XNTT_TRANSPOSE_TAG(TransposeSVEGatherVectorIndexColumnFirst)
 #undef XNTT_TRANSPOSE_TAG
 
 }  // namespace sventt

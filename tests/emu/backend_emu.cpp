@@ -38,6 +38,7 @@ static inline unsigned __brev(unsigned v) {
 #include "../../sve-ntt_b200/csrc/backend.h"
 #include "../../sve-ntt_b200/csrc/misc_kernels.cuh"
 #include "../../sve-ntt_b200/csrc/pass_kernel.cuh"
+#include "../../sve-ntt_b200/csrc/transpose_kernel.cuh"
 
 namespace xntt {
 
@@ -183,6 +184,31 @@ int launch_from_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, 
 }
 int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, size_t n, void*) {
   EMU_WITH_FIELD(fc, for (size_t i = 0; i < n; ++i) dst[i] = ew_mulnorm<F>(f, a[i], b[i]));
+  return 0;
+}
+int launch_transpose(u64* dst, const u64* src, u64 rows, u64 cols, u64 ld_dst, u64 ld_src, void*) {
+  const u64 tr = (rows + kTrTile - 1) / kTrTile, tc = (cols + kTrTile - 1) / kTrTile;
+  std::vector<u64> sa(kTrSmemWords), sb(kTrSmemWords);
+  if (dst == src) {
+    for (u64 i = 0; i < tc; ++i)
+      for (u64 j = i; j < tc; ++j) {
+        const u64 r0 = i * kTrTile, c0 = j * kTrTile;
+        for (int t = 0; t < kTrThreads; ++t) {
+          tr_load(dst, ld_dst, rows, cols, r0, c0, sa.data(), t);
+          if (i != j) tr_load(dst, ld_dst, rows, cols, c0, r0, sb.data(), t);
+        }
+        for (int t = 0; t < kTrThreads; ++t) {
+          tr_store(dst, ld_dst, rows, cols, r0, c0, sa.data(), t);
+          if (i != j) tr_store(dst, ld_dst, rows, cols, c0, r0, sb.data(), t);
+        }
+      }
+    return 0;
+  }
+  for (u64 a = 0; a < tr; ++a)
+    for (u64 b = 0; b < tc; ++b) {
+      for (int t = 0; t < kTrThreads; ++t) tr_load(src, ld_src, rows, cols, a * kTrTile, b * kTrTile, sa.data(), t);
+      for (int t = 0; t < kTrThreads; ++t) tr_store(dst, ld_dst, rows, cols, a * kTrTile, b * kTrTile, sa.data(), t);
+    }
   return 0;
 }
 int microbench(int, int, double*, double*) {

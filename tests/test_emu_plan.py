@@ -340,3 +340,24 @@ def test_sharded_peer_store_variants(emu, oracle, L, splits, G):
         got = np.empty(m // G, np.uint64)
         plans[r].shard_inverse_cols_chunk(got.ctypes.data, bufs2[r].ctypes.data, 0, 1)
         assert np.array_equal(got, blocks[r]), (L, splits, G, r)
+
+
+def test_transpose_contract(emu):
+    """Transpose*::transpose: dst[ld_dst*c + r] = src[ld_src*r + c] with padded leading dimensions
+    (tests/bench-transpose.cpp sweeps pads {0, 32}), ragged shapes, and the in-place square form."""
+    rng = np.random.default_rng(0)
+    for rows, cols, ps, pd in [(64, 64, 0, 0), (256, 512, 32, 0), (512, 256, 0, 32), (100, 37, 5, 3), (1, 1, 0, 0),
+                               (128, 4096, 32, 32), (63, 65, 0, 0)]:
+        src = rng.integers(0, 2**63, (rows, cols + ps), dtype=np.uint64)
+        dst = np.full((cols, rows + pd), 0x5555555555555555, dtype=np.uint64)
+        emu.transpose(dst.ctypes.data, src.ctypes.data, rows, cols, rows + pd, cols + ps)
+        assert np.array_equal(dst[:, :rows], src[:, :cols].T)
+        assert (dst[:, rows:] == 0x5555555555555555).all()  # padding untouched
+        back = np.empty_like(src)
+        emu.transpose(back.ctypes.data, dst.ctypes.data, cols, rows, cols + ps, rows + pd)
+        assert np.array_equal(back[:, :cols], src[:, :cols])  # the reference's iota round-trip check
+    for dim, pad in [(64, 0), (200, 8), (1, 0), (513, 0)]:
+        a = rng.integers(0, 2**63, (dim, dim + pad), dtype=np.uint64)
+        b = a.copy()
+        emu.transpose(b.ctypes.data, b.ctypes.data, dim, dim, dim + pad, dim + pad)
+        assert np.array_equal(b[:, :dim], a[:, :dim].T)

@@ -348,3 +348,24 @@ def test_fused_forward_multiply(cuda_lib, oracle, L, splits, N, g):
         want = oracle.pointwise_mul(oracle.ntt_forward(a, N, g), oracle.ntt_forward(b, N, g), N)
         assert np.array_equal(host(fused), want)
     plan.close()
+
+
+def test_transpose_contract(cuda_lib):
+    """tests/bench-transpose.cpp: every shape transposed and transposed back must return the input;
+    sizes 2^8..2^13, pads {0, 32}, plus ragged shapes and the in-place square form."""
+    import torch
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(3)
+    shapes = [(1 << a, 1 << b, ps, pd) for a in (8, 10, 13) for b in (8, 11, 13) for ps, pd in ((0, 0), (32, 32))]
+    shapes += [(100, 37, 5, 3), (63, 65, 0, 0), (1, 1, 0, 0), (4096, 4096, 0, 0)]
+    for rows, cols, ps, pd in shapes:
+        src = torch.randint(0, 2**62, (rows, cols + ps), dtype=torch.int64, device="cuda", generator=gen)
+        dst = torch.full((cols, rows + pd), 0x55, dtype=torch.int64, device="cuda")
+        cuda_lib.transpose(dst.data_ptr(), src.data_ptr(), rows, cols, rows + pd, cols + ps, stream())
+        assert torch.equal(dst[:, :rows], src[:, :cols].t())
+        assert bool((dst[:, rows:] == 0x55).all())
+    for dim, pad in [(64, 0), (200, 8), (2048, 0), (513, 0)]:
+        a = torch.randint(0, 2**62, (dim, dim + pad), dtype=torch.int64, device="cuda", generator=gen)
+        b = a.clone()
+        cuda_lib.transpose(b.data_ptr(), b.data_ptr(), dim, dim, dim + pad, dim + pad, stream())
+        assert torch.equal(b[:, :dim], a[:, :dim].t())
