@@ -61,6 +61,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload, splits, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
+    ncu --set full capture of this very command (profiles/r1_v2_ncu_pass_kernels.json); None when the
+    capture does not cover the configuration."""
+    path = os.path.join(ROOT, "profiles", "r1_v2_ncu_pass_kernels.json")
+    if workload != "ntt24" or list(splits) != [11, 13] or not os.path.exists(path):
+        return None
+    order = ["fwd_pass0_2^11", "fwd_pass1_2^13", "inv_pass1_2^13", "inv_pass0_2^11"]  # launch order in the capture
+    if kernel not in order:
+        return None
+    with open(path) as fh:
+        k = json.load(fh)["kernels"][order.index(kernel)]
+    return (float(k["dram__bytes_read.sum [Mbyte]"]) + float(k["dram__bytes_write.sum [Mbyte]"])) * 1e6
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks: NVML sampled in a thread during the timed region
 class ClockSampler:
@@ -286,7 +301,8 @@ def main():
                                    "us": us, "alg_gbs": 16.0 * local_words / (us * 1e-6) / 1e9})
         dom = max(per_kernel, key=lambda k: k["us"])
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["alg_gbs"], "peak": hbm_peak,
-                    "unit": "GB/s", "frac": dom["alg_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": dom["alg_gbs"] / hbm_peak, "traffic": ncu_traffic(w, plan.splits, dom["kernel"]),
+                    "peak_source": peak_src,
                     "alg_bytes_per_launch": 16 * local_words,
                     "note": "kernel reads and writes every residue once: 16 B/element per launch; the kernels are "
                             "bound by the IMAD pipe, see roofline_int"}

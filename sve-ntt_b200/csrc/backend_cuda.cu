@@ -288,8 +288,8 @@ int launch_transpose(u64* dst, const u64* src, u64 rows, u64 cols, u64 ld_dst, u
     attr_done = true;
   }
   if (dst == src) {
-    const u64 t = p.tiles_c, pairs = t * (t + 1) / 2;
-    transpose_inplace_kernel<<<(unsigned)pairs, kTrThreads, 2 * kTrSmemWords * sizeof(u64), (cudaStream_t)stream>>>(p);
+    const dim3 grid2(p.tiles_c, p.tiles_c);
+    transpose_inplace_kernel<<<grid2, kTrThreads, 2 * kTrSmemWords * sizeof(u64), (cudaStream_t)stream>>>(p);
   } else {
     transpose_kernel<<<(unsigned)(tiles_r * p.tiles_c), kTrThreads, kTrSmemWords * sizeof(u64),
                        (cudaStream_t)stream>>>(p);

@@ -58,16 +58,13 @@ __global__ void __launch_bounds__(kTrThreads) transpose_kernel(const __grid_cons
   tr_store(p.dst, p.ld_dst, p.rows, p.cols, r0, c0, sm, threadIdx.x);
 }
 
-// in place, square: CTA (i, j), i <= j, swaps tile (i, j) with tile (j, i)
+// in place, square: CTA (i, j) of a 2-D grid swaps tile (i, j) with tile (j, i); the lower triangle exits
 __global__ void __launch_bounds__(kTrThreads) transpose_inplace_kernel(const __grid_constant__ TransposeParams p) {
   extern __shared__ __align__(16) unsigned char tr_smem_raw[];
   u64* sa = reinterpret_cast<u64*>(tr_smem_raw);
   u64* sb = sa + kTrSmemWords;
-  // unrank the upper-triangular pair index
-  const u32 t = p.tiles_c;
-  u32 i = 0, rem = blockIdx.x;
-  while (rem >= t - i) rem -= t - i, ++i;
-  const u32 j = i + rem;
+  const u32 i = blockIdx.y, j = blockIdx.x;
+  if (i > j) return;
   const u64 r0 = (u64)i * kTrTile, c0 = (u64)j * kTrTile;
   tr_load(p.dst, p.ld_dst, p.rows, p.cols, r0, c0, sa, threadIdx.x);
   if (i != j) tr_load(p.dst, p.ld_dst, p.rows, p.cols, c0, r0, sb, threadIdx.x);
