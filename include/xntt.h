@@ -39,7 +39,13 @@ typedef enum xntt_status {
   XNTT_ERR_STATE = -5        /* direction not enabled in this plan (reference: std::logic_error)   */
 } xntt_status;
 
-enum { XNTT_ENABLE_FORWARD = 1, XNTT_ENABLE_INVERSE = 2 };
+enum {
+  XNTT_ENABLE_FORWARD = 1,
+  XNTT_ENABLE_INVERSE = 2,
+  /* keep the six-step twiddles as two sqrt(M)-entry tables (two modular products per residue) even where
+   * the planner would store the whole twiddle matrix (16 bytes per residue and direction, one product) */
+  XNTT_COMPACT_TABLES = 4
+};
 
 #define XNTT_MAX_SPLITS 4
 
@@ -53,7 +59,7 @@ typedef struct xntt_desc {
   uint32_t batch;          /* number of back-to-back transforms in one buffer (0 means 1)           */
   uint64_t inverse_factor; /* inverse output is divided by this (0 or 1: unscaled); the reference's */
                            /* inverse_factor layer argument (layer/sve/radix-eight.hpp:19)          */
-  uint32_t flags;          /* XNTT_ENABLE_*; 0 means both (wrapper.hpp:34-35)                        */
+  uint32_t flags;          /* XNTT_ENABLE_* (neither bit = both, wrapper.hpp:34-35) | XNTT_COMPACT_TABLES */
   int32_t device;          /* CUDA device ordinal, -1 = current                                     */
   uint32_t n_splits;       /* 0 = let the planner decompose m; else the six-step decomposition      */
   uint32_t split_log2[XNTT_MAX_SPLITS]; /* m = prod 2^split_log2[i], outermost (column) first       */

@@ -17,7 +17,7 @@ P0 = 0xFFFFFC6E80000001  # 2^64 - 1827*2^31 + 1 (reference README.md:19)
 G0 = 3
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_ALLOC, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5
-ENABLE_FORWARD, ENABLE_INVERSE = 1, 2
+ENABLE_FORWARD, ENABLE_INVERSE, COMPACT_TABLES = 1, 2, 4
 MAX_SPLITS = 4
 
 
@@ -135,13 +135,15 @@ class Plan:
     """sventt::NTT<kernel> (include/sventt/wrapper.hpp:13-83) over raw pointers."""
 
     def __init__(self, library, log2_m, modulus=P0, generator=G0, batch=1, inverse_factor=None,
-                 forward=True, inverse=True, device=-1, splits=None, shard_count=0, shard_rank=0):
+                 forward=True, inverse=True, device=-1, splits=None, shard_count=0, shard_rank=0,
+                 compact_tables=False):
         self.L = library
         d = Desc()
         d.modulus, d.generator = modulus, generator
         d.log2_m, d.batch = log2_m, batch
         d.inverse_factor = (1 << log2_m) if inverse_factor is None else inverse_factor
-        d.flags = (ENABLE_FORWARD if forward else 0) | (ENABLE_INVERSE if inverse else 0)
+        d.flags = (ENABLE_FORWARD if forward else 0) | (ENABLE_INVERSE if inverse else 0) | \
+            (COMPACT_TABLES if compact_tables else 0)
         d.device = device
         if splits:
             d.n_splits = len(splits)

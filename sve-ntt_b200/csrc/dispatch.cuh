@@ -21,19 +21,44 @@ cudaError_t launch_inv_row_rt(int logn, const PassParams& prm, unsigned grid, cu
 cudaError_t launch_fwd_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 
-template <class F, int LOGN, bool COL, bool INV, bool MAP = false>
-cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
+template <class F, int LOGN, bool COL, bool INV, bool MAP, int TWIST>
+cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st) {
   constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
-  auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, COL, MAP>;
+  auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, TWIST, MAP>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
+#ifndef XNTT_CARVE_TILES
+#define XNTT_CARVE_TILES XNTT_MINB
+#endif
+#if XNTT_CARVE_TILES > 2
+    // room for XNTT_MINB resident tiles and not more: what is left of the 228 KiB stays L1, which the twiddle
+    // tables live in (measured: 2^24 forward 433 us with the default split, 506 us with L1 squeezed to 32 KiB)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)((XNTT_CARVE_TILES * (Cfg::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+    if (e != cudaSuccess) return e;
+#endif
     attr_done = true;
   }
   kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(prm);
   return cudaGetLastError();
+}
+
+// Column passes carry the six-step twiddle in one of two forms (pass_kernel.cuh: apply_twist); the generalised-
+// addressing kernels of sharded plans only exist in the compact form (the planner never gives them a full matrix).
+template <class F, int LOGN, bool COL, bool INV, bool MAP = false>
+cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
+  if constexpr (!COL) {
+    return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
+  } else if constexpr (MAP) {
+    if (prm.twist_full != nullptr) return cudaErrorInvalidValue;
+    return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist>(prm, grid, st);
+  } else {
+    if (prm.twist_full != nullptr) return launch_kernel<F, LOGN, COL, INV, MAP, kFullTwist>(prm, grid, st);
+    return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist>(prm, grid, st);
+  }
 }
 
 #define XNTT_CASE(F, L, COL, INV) \

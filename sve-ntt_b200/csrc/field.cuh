@@ -184,15 +184,18 @@ struct FieldOps : K {
     const u32 carry2 = lh < (u32)y ? 1u : 0u;
     h2 = (u64)q1 * P_HI + ((y >> 32) | ((u64)yc << 32)) + carry2;
 #else
-    u32 a0, a1, w0, w1, q0, q1, h1l, h1h, h2l, h2h;
+    u32 a0, a1, w0, w1, q0, q1, h1l, h1h, h2l, h2h, vl, vh;
     unpack64(a, a0, a1);
     unpack64(w, w0, w1);
     unpack64(a * wp, q0, q1);
-    asm("{\n\t.reg .u32 xl, xh, xc, vh, lh, yl, yh, yc, t;\n\t"
+    // a0*w0 as a full IMAD.WIDE: costs the fma pipe what IMAD.HI does, but spares the (0 : xl) addend pair
+    // ptxas builds for the IMAD.HI form (butterfly loop: 53.2 instead of 55.2 fma-pipe cycles, measured 3 % faster)
+    unpack64((u64)a0 * w0, vl, vh);
+    (void)vl;
+    asm("{\n\t.reg .u32 xl, xh, xc, lh, yl, yh, yc, t;\n\t"
         "mul.lo.u32 xl, %4, %7;\n\tmul.hi.u32 xh, %4, %7;\n\t"  // a0*w1
         "mad.lo.cc.u32 xl, %5, %6, xl;\n\tmadc.hi.cc.u32 xh, %5, %6, xh;\n\taddc.u32 xc, 0, 0;\n\t"  // + a1*w0
-        "mul.hi.u32 vh, %4, %6;\n\t"     // hi32(a0*w0)
-        "add.cc.u32 lh, xl, vh;\n\t"     // L.hi, carry1
+        "add.cc.u32 lh, xl, %12;\n\t"    // L.hi, carry1
         "madc.lo.cc.u32 %0, %5, %7, xh;\n\tmadc.hi.u32 %1, %5, %7, xc;\n\t"  // h1 = a1*w1 + {xh, xc} + carry1
         "mul.lo.u32 yl, %8, %11;\n\tmul.hi.u32 yh, %8, %11;\n\t"  // q0*P1
         "mad.lo.cc.u32 yl, %9, %10, yl;\n\tmadc.hi.cc.u32 yh, %9, %10, yh;\n\taddc.u32 yc, 0, 0;\n\t"  // + q1*P0
@@ -202,7 +205,7 @@ struct FieldOps : K {
         "madc.lo.cc.u32 %2, %9, %11, yh;\n\tmadc.hi.u32 %3, %9, %11, yc;\n\t"  // h2 = q1*P1 + {yh, yc} + carry2
         "}"
         : "=r"(h1l), "=r"(h1h), "=r"(h2l), "=r"(h2h)
-        : "r"(a0), "r"(a1), "r"(w0), "r"(w1), "r"(q0), "r"(q1), "r"(P_LO), "r"(P_HI));
+        : "r"(a0), "r"(a1), "r"(w0), "r"(w1), "r"(q0), "r"(q1), "r"(P_LO), "r"(P_HI), "r"(vh));
     h1 = pack64(h1l, h1h);
     h2 = pack64(h2l, h2h);
 #endif

@@ -42,6 +42,11 @@ __device__ __forceinline__ u32 table_exponent(u32 idx, int kind, int logn, int s
     const int ll = 31 - clz32(idx);  // log2 l
     return (idx - (1u << ll)) << (logn - 1 - ll);
   }
+  if (kind == kTwist) {
+    // twist matrix entry (k, c), idx = (k << shift) + c: omega_M^(bitrev_logn(k) * c), M = 2^(logn + shift)
+    const u32 k = idx >> shift, c = idx & ((1u << shift) - 1u);
+    return (logn ? (brev32(k) >> (32 - logn)) : 0u) * c;
+  }
   return idx << shift;
 }
 

@@ -59,10 +59,13 @@ struct PassParams {
   const Tw* tw;        // forward: G[0 .. N/2), inverse: I[1 .. N)
   const Tw* twist_lo;  // omega_M^(+-e), e < 2^twist_shift            (null when no twist)
   const Tw* twist_hi;  // omega_M^(+-e * 2^twist_shift) (* 1/inverse_factor on the inverse side)
+  const Tw* twist_full;  // optional: the whole twiddle matrix, entry (k << twist_full_shift) + column; when set
+                         // the twist is one streamed 16-byte load and one Montgomery product per residue
   u64 inner;           // column mode: elements between consecutive k; row mode: unused
   u64 outer_stride;    // column mode: elements between consecutive outer blocks (= N * inner)
   u32 tiles_per_outer; // column mode: inner / W
   u32 twist_shift;
+  u32 twist_full_shift;  // log2 of the number of columns of twist_full
   u32 twist_col0;      // column mode: global index of this buffer's first column (sharded plans)
   u32 scale_on;        // inverse row mode: multiply outputs by `scale` (else just canonicalise)
   u32 rows;            // row mode: number of valid rows in the buffer (tiles may be ragged)
@@ -83,6 +86,6 @@ struct PowTable {
   u64 sq[32];  // root^(2^i) in Montgomery form
   u64 scale;   // Montgomery form of the extra factor (2^64 mod P for none)
 };
-enum TableKind { kFwdG = 0, kInvI = 1, kPowers = 2 };
+enum TableKind { kFwdG = 0, kInvI = 1, kPowers = 2, kTwist = 3 };
 
 }  // namespace xntt

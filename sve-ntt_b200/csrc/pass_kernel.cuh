@@ -36,6 +36,8 @@
 
 namespace xntt {
 
+enum TwistKind { kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2 };
+
 template <int LOGN>
 struct Stages {
   static constexpr int kRem = LOGN % 3;
@@ -244,14 +246,96 @@ __device__ __forceinline__ Tw ld_tw(const Tw* t) {
   return r;
 }
 
-// Six-step twiddle of element (k, global column col): omega_M^(bitrev_LOGN(k) * col), looked up as
-// hi[e >> shift] * lo[e & mask] and applied as two Montgomery products (canonical result).
-template <class F, int LOGN>
-__device__ __forceinline__ u64 apply_twist(const F& f, const PassParams& prm, u64 v, int k, u32 col) {
-  const u32 e = (__brev((u32)k) >> (32 - LOGN)) * col;
-  const Tw lo = ld_tw(prm.twist_lo + (e & ((1u << prm.twist_shift) - 1u)));
-  const Tw hi = ld_tw(prm.twist_hi + (e >> prm.twist_shift));
-  return f.mont(f.mont(v, hi), lo);
+// Hint the twiddles a later stage will use into L1 (no register cost): the last stages read one table entry per
+// butterfly, and with 4 warps per scheduler an L1 miss there is exposed latency.
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#if !defined(XNTT_HOST_EMU)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if !defined(XNTT_HOST_EMU)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+#ifndef XNTT_PREFETCH_TW
+#define XNTT_PREFETCH_TW 0
+#endif
+
+// forward stage J's twiddles of this thread's tasks: G[(B << lam) + g], lam < LOGR, g < 2^lam
+template <class Cfg, int J>
+__device__ __forceinline__ void prefetch_fwd_stage(const Tw* __restrict__ G) {
+  constexpr int NS = Cfg::NS;
+  constexpr int LOGR = (J == 0) ? Cfg::LOGR1 : 3;
+  constexpr int LOGS = 3 * (NS - 1 - J);
+  constexpr int LOGT = Cfg::LOGN - LOGR;
+  constexpr int NTASK = (1 << LOGT) * Cfg::NP;
+  if constexpr (LOGS <= 3) {  // earlier stages share each entry between >= 64 tasks: nothing to hide
+#pragma unroll 1
+    for (int task = threadIdx.x; task < NTASK; task += kThreads) {
+      int t;
+      if constexpr (Cfg::COL)
+        t = task >> Cfg::LOGNP;
+      else
+        t = task & ((1 << LOGT) - 1);
+      const int B = t >> LOGS;
+#pragma unroll
+      for (int lam = 0; lam < LOGR; ++lam) {
+        // 2^lam consecutive 16-byte entries: one 128-byte line holds 8
+#pragma unroll
+        for (int g = 0; g < (1 << lam); g += 8) prefetch_l1(G + ((B << lam) + g));
+      }
+    }
+  }
+}
+
+// Six-step twiddle of element (k, global column col): omega_M^(bitrev_LOGN(k) * col).  Two forms:
+//   * prm.twist_full set: the plan holds the whole twiddle matrix in the layout of the data (entry (k, col)
+//     next to entry (k, col + 1)); the twist is one streamed load and ONE Montgomery product.  The load is as
+//     coalesced as the tile store itself and never touches L1 (the random hi/lo look-ups below are what made the
+//     kernels L1-size sensitive: 2^24 forward 433 -> 506 us when L1 shrinks from 96 to 32 KiB).
+//   * otherwise hi[e >> shift] * lo[e & mask], two Montgomery products (any size, tables of 2 * sqrt(M) entries).
+// Both results are canonical.
+__device__ __forceinline__ Tw ld_tw_stream(const Tw* t) {
+#if !defined(XNTT_HOST_EMU)
+  Tw r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.w), "=l"(r.wp) : "l"(t));
+  return r;
+#else
+  return *t;
+#endif
+}
+// all R x C residues of a task; the table form is a template parameter (a run-time test costs the compact form
+// 3.5 %: 2^24 forward 446 instead of 430 us)
+template <class F, class Cfg, int R, int TWIST>
+__device__ __forceinline__ void apply_twist(const F& f, const PassParams& prm, u64 (&x)[R][Cfg::C], int k0, int logs,
+                                            u32 col) {
+  if constexpr (TWIST == kFullTwist) {
+    Tw t[R][Cfg::C];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < Cfg::C; ++c)
+        t[r][c] = ld_tw_stream(prm.twist_full + (((u64)(u32)(k0 + (r << logs)) << prm.twist_full_shift) + (col + c)));
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], t[r][c]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < Cfg::C; ++c) {
+        const u32 e = (__brev((u32)(k0 + (r << logs))) >> (32 - Cfg::LOGN)) * (col + c);
+        const Tw lo = ld_tw(prm.twist_lo + (e & ((1u << prm.twist_shift) - 1u)));
+        const Tw hi = ld_tw(prm.twist_hi + (e >> prm.twist_shift));
+        x[r][c] = f.mont(f.mont(x[r][c], hi), lo);
+      }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -316,7 +400,7 @@ __device__ __forceinline__ void inv_network(const F& f, u64 (&x)[1 << LOGR][C], 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <class F, class Cfg, bool TWIST, int J>
+template <class F, class Cfg, int TWIST, int J>
 __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
                                           const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
   const F f = make_field<F>(prm.field);
@@ -326,6 +410,9 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
   constexpr int LOGS = 3 * (NS - 1 - J);
   constexpr int LOGT = Cfg::LOGN - LOGR;  // tasks per sub-transform
   constexpr int NTASK = (1 << LOGT) * Cfg::NP;
+#if XNTT_PREFETCH_TW
+  if constexpr (J + 1 < NS) prefetch_fwd_stage<Cfg, J + 1>(prm.tw);
+#endif
 #pragma unroll 1
   for (int task = threadIdx.x; task < NTASK; task += kThreads) {
     int p, t;
@@ -345,12 +432,12 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
       smem_load<Cfg, R>(sm, k0, LOGS, p, x);
     fwd_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, B);
     if constexpr (J == NS - 1) {
+      if constexpr (TWIST != kNoTwist) apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < Cfg::C; ++c) {
-          if constexpr (TWIST) {
-            x[r][c] = apply_twist<F, Cfg::LOGN>(f, prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
+          if constexpr (TWIST != kNoTwist) {
           } else if (prm.pointwise != nullptr) {
             // fused point-wise product of a polynomial multiply
             // (examples/magic-series/gaussian-polynomial.hpp:201-212); the Montgomery product is canonical
@@ -368,7 +455,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
   if constexpr (J != NS - 1) __syncthreads();
 }
 
-template <class F, class Cfg, bool TWIST, int J>
+template <class F, class Cfg, int TWIST, int J>
 __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
                                           const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
   const F f = make_field<F>(prm.field);
@@ -394,13 +481,7 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
     u64 x[R][Cfg::C];
     if constexpr (J == 0) {
       gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
-      if constexpr (TWIST) {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int c = 0; c < Cfg::C; ++c)
-            x[r][c] = apply_twist<F, Cfg::LOGN>(f, prm, x[r][c], k0 + (r << LOGS), col0 + p * Cfg::C + c);
-      }
+      if constexpr (TWIST != kNoTwist) apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
     } else {
       smem_load<Cfg, R>(sm, k0, LOGS, p, x);
     }
@@ -425,7 +506,7 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
   if constexpr (J != NS - 1) __syncthreads();
 }
 
-template <class F, class Cfg, bool INVERSE, bool TWIST, int... Js>
+template <class F, class Cfg, bool INVERSE, int TWIST, int... Js>
 __device__ __forceinline__ void run_stages(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
                                            const u64* gsrc, u64* gdst, u32 col0, u32 row0,
                                            std::integer_sequence<int, Js...>) {
@@ -460,7 +541,12 @@ __device__ __forceinline__ void tile_origin(const PassParams& prm, u32 tile, u64
 }
 
 #if !defined(XNTT_HOST_EMU)
-template <class F, int LOGN, int LOGW, int C, bool COL, bool INVERSE, bool TWIST, bool MAP = false>
+// Distance (in tiles) of the L2 prefetch each CTA issues for a tile that will start soon (0 = off).
+#ifndef XNTT_PREFETCH_TILE
+#define XNTT_PREFETCH_TILE 0
+#endif
+
+template <class F, int LOGN, int LOGW, int C, bool COL, bool INVERSE, int TWIST, bool MAP = false>
 __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_constant__ PassParams prm) {
   typedef PassCfg<LOGN, LOGW, C, COL, MAP> Cfg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -468,7 +554,37 @@ __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_
   const u32 tile = blockIdx.x;
   u64 sbase, dbase;
   u32 col0 = 0, row0 = 0;
+#if XNTT_PREFETCH_TILE > 0
+  if constexpr (!MAP) {
+    const u32 nt = tile + XNTT_PREFETCH_TILE;
+    if (nt < gridDim.x) {
+      u64 sb, db;
+      u32 c0 = 0, r0 = 0;
+      tile_origin<Cfg>(prm, nt, sb, db, c0, r0);
+      const u64* q = prm.src + sb;
+      if constexpr (COL) {
+        // N row segments of W words each
+        for (int k = threadIdx.x; k < Cfg::N; k += kThreads)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (u64)k * prm.inner));
+      } else {
+        // contiguous: one 128-byte line per prefetch
+        for (int l = threadIdx.x; l < (Cfg::N * Cfg::W) / 16; l += kThreads)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (u64)l * 16));
+      }
+    }
+  }
+#endif
   tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
+  if constexpr (TWIST == kFullTwist && !INVERSE) {
+    // forward: the twiddle matrix is consumed by the last stage - start pulling this tile's N segments of it
+    // (W entries = 16 W bytes each) into L2 now, so that the streamed loads there do not wait for HBM
+    {
+      const Tw* q = prm.twist_full + col0;
+      constexpr int SEG = Cfg::W >= 2 ? Cfg::W / 2 : 1;  // 32-byte sectors per segment
+      for (int i = threadIdx.x; i < Cfg::N * SEG; i += kThreads)
+        prefetch_l2(q + (((u64)(i / SEG) << prm.twist_full_shift) + (u64)(i % SEG) * 2));
+    }
+  }
   run_stages<F, Cfg, INVERSE, TWIST>(prm, sm, prm.src + sbase, prm.dst + dbase, col0, row0,
                                      std::make_integer_sequence<int, Cfg::NS>{});
 }

@@ -15,6 +15,7 @@
 // The inverse runs the same passes backwards with inverse tables; 1/inverse_factor is folded into
 // the outermost pass's twiddle table (or applied at the end of a single-pass inverse).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -38,6 +39,9 @@ struct PassDesc {
   const Tw* fwd_hi = nullptr;
   const Tw* inv_lo = nullptr;
   const Tw* inv_hi = nullptr;
+  // whole twiddle matrix [N][inner] (one Montgomery product per residue instead of two), when it fits the budget
+  const Tw* fwd_full = nullptr;
+  const Tw* inv_full = nullptr;
 };
 
 struct xntt_plan {
@@ -149,6 +153,8 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.twist_lo = inverse ? ps.inv_lo : ps.fwd_lo;
     prm.twist_hi = inverse ? ps.inv_hi : ps.fwd_hi;
     prm.twist_shift = (u32)ps.twist_shift;
+    prm.twist_full = inverse ? ps.inv_full : ps.fwd_full;
+    prm.twist_full_shift = (u32)ps.log_inner;
     prm.twist_col0 = sharded_first ? (u32)(inner * pl->shard_rank) : 0u;
     const u64 tiles = outer * prm.tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -282,6 +288,8 @@ int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const
     prm.twist_lo = inverse ? ps.inv_lo : ps.fwd_lo;
     prm.twist_hi = inverse ? ps.inv_hi : ps.fwd_hi;
     prm.twist_shift = (u32)ps.twist_shift;
+    prm.twist_full = inverse ? ps.inv_full : ps.fwd_full;
+    prm.twist_full_shift = (u32)ps.log_inner;
     prm.twist_col0 = twist_col0;
     const u64 tiles = units * tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -382,7 +390,8 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   pl->desc = *d;
   pl->log2_m = (int)d->log2_m;
   pl->batch = d->batch ? d->batch : 1;
-  const u32 flags = d->flags ? d->flags : (XNTT_ENABLE_FORWARD | XNTT_ENABLE_INVERSE);
+  const u32 dirs = d->flags & (XNTT_ENABLE_FORWARD | XNTT_ENABLE_INVERSE);
+  const u32 flags = dirs ? dirs : (XNTT_ENABLE_FORWARD | XNTT_ENABLE_INVERSE);
   pl->fwd = (flags & XNTT_ENABLE_FORWARD) != 0;
   pl->inv = (flags & XNTT_ENABLE_INVERSE) != 0;
   pl->shard_count = shard_count;
@@ -416,6 +425,16 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   pl->passes.resize(q);
   size_t words = 0;
   std::vector<size_t> off_fwd(q), off_inv(q), off_flo(q), off_fhi(q), off_ilo(q), off_ihi(q);
+  std::vector<size_t> off_ffull(q, 0), off_ifull(q, 0);
+  std::vector<char> use_full(q, 0);
+  // Whole-matrix twiddles: every column pass whose matrix (N * inner entries of 16 bytes per enabled direction)
+  // still fits the budget, outermost first.  Default 128 MiB: matrices that stay L2-resident next to the data
+  // (batched 2^20: +4 %, the inner matrix of 2^28: +2 %); at 2^24 the 256 MiB-per-direction matrix only breaks
+  // even with the compact form (forward 441 vs 430 us, inverse 429 vs 445 us), so it is not worth its memory.
+  // XNTT_TWIST_TABLE_MAX_MB overrides; sharded plans and XNTT_COMPACT_TABLES keep the compact form.
+  size_t full_budget = (size_t)128 << 20;
+  if (const char* e = std::getenv("XNTT_TWIST_TABLE_MAX_MB")) full_budget = (size_t)std::strtoull(e, nullptr, 10) << 20;
+  if ((d->flags & XNTT_COMPACT_TABLES) || shard_count > 1) full_budget = 0;
   {
     int rem = pl->log2_m, before = 0;
     for (size_t i = 0; i < q; ++i) {
@@ -443,6 +462,19 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
         words += nlo;
         off_ihi[i] = words;
         words += nhi;
+        const size_t cells = (size_t)1 << lm, dirs_n = (pl->fwd ? 1 : 0) + (pl->inv ? 1 : 0);
+        if (lm <= 31 && cells * dirs_n * sizeof(Tw) <= full_budget) {
+          full_budget -= cells * dirs_n * sizeof(Tw);
+          use_full[i] = 1;
+          if (pl->fwd) {
+            off_ffull[i] = words;
+            words += cells;
+          }
+          if (pl->inv) {
+            off_ifull[i] = words;
+            words += cells;
+          }
+        }
       }
     }
   }
@@ -480,6 +512,18 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
       // the outermost column pass runs last in the inverse: fold 1/inverse_factor into its table
       if (rc == XNTT_OK)
         rc = gen_table(pl->field, base + off_ihi[i], nhi, kPowers, 0, ps.twist_shift, root_big_inv, i == 0 ? finv : 1);
+      if (use_full[i]) {
+        const u32 cells = 1u << lm;
+        if (pl->fwd && rc == XNTT_OK) {
+          ps.fwd_full = base + off_ffull[i];
+          rc = gen_table(pl->field, base + off_ffull[i], cells, kTwist, ps.logn, ps.log_inner, root_big, 1);
+        }
+        if (pl->inv && rc == XNTT_OK) {
+          ps.inv_full = base + off_ifull[i];
+          rc = gen_table(pl->field, base + off_ifull[i], cells, kTwist, ps.logn, ps.log_inner, root_big_inv,
+                         i == 0 ? finv : 1);
+        }
+      }
     }
   }
   if (rc == XNTT_OK) {

@@ -42,7 +42,7 @@ static inline unsigned __brev(unsigned v) {
 
 namespace xntt {
 
-template <class F, class Cfg, bool INV, bool TWIST, int J>
+template <class F, class Cfg, bool INV, int TWIST, int J>
 static void emu_stage_all_threads(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc,
                                   u64* gdst, u32 col0, u32 row0) {
   for (unsigned t = 0; t < (unsigned)kThreads; ++t) {
@@ -54,7 +54,7 @@ static void emu_stage_all_threads(const PassParams& prm, typename Slot<Cfg::C>::
   }
 }
 
-template <class F, class Cfg, bool INV, bool TWIST, int... Js>
+template <class F, class Cfg, bool INV, int TWIST, int... Js>
 static void emu_stages(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc, u64* gdst,
                        u32 col0, u32 row0, std::integer_sequence<int, Js...>) {
   // a stage ends with a block-wide barrier: run every emulated thread through stage J, then J + 1
@@ -73,8 +73,16 @@ static int emu_launch2(const PassParams& prm, unsigned grid) {
     tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
     // poison shared memory so that a missing write shows up
     memset(sm.data(), 0xcd, sm.size() * sizeof(sm[0]));
-    emu_stages<F, Cfg, INV, COL>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
-                              std::make_integer_sequence<int, Cfg::NS>{});
+    // same choice of the twist form as dispatch.cuh: launch_one
+    if (!COL)
+      emu_stages<F, Cfg, INV, kNoTwist>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
+                                        std::make_integer_sequence<int, Cfg::NS>{});
+    else if (prm.twist_full != nullptr && !MAP)
+      emu_stages<F, Cfg, INV, kFullTwist>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
+                                          std::make_integer_sequence<int, Cfg::NS>{});
+    else
+      emu_stages<F, Cfg, INV, kCompactTwist>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
+                                             std::make_integer_sequence<int, Cfg::NS>{});
   }
   return 0;
 }

@@ -9,10 +9,10 @@ import pytest
 from conftest import G0, P0, SEED
 
 
-def roundtrip(emu, oracle, L, splits=None, batch=1, inverse_factor=None):
+def roundtrip(emu, oracle, L, splits=None, batch=1, inverse_factor=None, **kw):
     m = 1 << L
     a = oracle.fill_xorshift(m * batch, SEED + L, P0)
-    plan = emu.plan(L, splits=splits, batch=batch, inverse_factor=inverse_factor)
+    plan = emu.plan(L, splits=splits, batch=batch, inverse_factor=inverse_factor, **kw)
     out = np.empty_like(a)
     plan.forward(out.ctypes.data, a.ctypes.data)
     for b in range(batch):
@@ -49,6 +49,16 @@ def test_default_two_pass(emu, oracle, L):
 ])
 def test_explicit_splits(emu, oracle, L, splits):
     assert roundtrip(emu, oracle, L, splits=splits) == splits
+
+
+@pytest.mark.parametrize("L,splits", [(14, None), (17, [8, 9]), (16, [5, 5, 6]), (13, [1, 12])])
+def test_compact_twiddle_tables(emu, oracle, L, splits, monkeypatch):
+    """The six-step twiddles exist in two forms (whole matrix / two sqrt(M) tables, XNTT_COMPACT_TABLES): the
+    default plans above run the first, these the second - by flag and by a zero table budget."""
+    assert len(roundtrip(emu, oracle, L, splits=splits, compact_tables=True)) >= 2
+    roundtrip(emu, oracle, L, splits=splits, compact_tables=True, inverse_factor=777)
+    monkeypatch.setenv("XNTT_TWIST_TABLE_MAX_MB", "0")
+    roundtrip(emu, oracle, L, splits=splits)
 
 
 @pytest.mark.parametrize("L,batch", [(3, 1), (3, 33), (6, 5), (10, 7), (12, 3), (13, 2), (15, 3)])

@@ -1,0 +1,172 @@
+// SPDX-License-Identifier: Apache-2.0
+// Development lab (not part of the product): register-resident butterfly loops for candidate PAdic64
+// butterfly formulations.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I../../sve-ntt_b200/csrc
+// bfly_lab.cu -o bfly_lab ; static pipe estimate: cuobjdump -sass + sasscount.py.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "field.cuh"
+#include "field2.cuh"
+
+using namespace xntt;
+
+template <int V>
+__device__ __forceinline__ void bfly(u64& x0, u64& x1, u64 w, u64 wp) {
+  if constexpr (V == 0) {
+    const F0 f{};
+    f.ct_butterfly(x0, x1, w, wp);
+  } else if constexpr (V == 1) {
+    lab::bf_v1(x0, x1, w, wp);
+  } else if constexpr (V == 2) {
+    lab::bf_v2(x0, x1, w, wp);
+  } else if constexpr (V == 3) {
+    lab::bf_v3(x0, x1, w, wp);
+  } else if constexpr (V == 4) {
+    lab::bf_v4(x0, x1, w, wp);
+  } else if constexpr (V == 5) {
+    lab::bf_v5(x0, x1, w, wp);
+  } else if constexpr (V == 6) {
+    lab::bf_v6(x0, x1, w, wp);
+  } else if constexpr (V == 7) {
+    lab::bf_v7(x0, x1, w, wp);
+  } else if constexpr (V == 8) {
+    lab::bf_v8(x0, x1, w, wp);
+  } else if constexpr (V == 9) {
+    lab::bf_mixed<0>(x0, x1, w, wp);
+  } else if constexpr (V == 10) {
+    lab::bf_mixed<1>(x0, x1, w, wp);
+  } else if constexpr (V == 11) {
+    lab::bf_mixed<3>(x0, x1, w, wp);
+  }
+}
+
+// 16 values per thread = 8 independent butterflies per level, 4 levels of a radix-16 network per iteration
+// (indices permuted between levels so that values really mix, as in the kernel)
+template <int V, int MINB>
+__global__ void __launch_bounds__(256, MINB) loop_kernel(u64* out, const u64* in, const Tw* tw, int iters) {
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+  u64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = in[(tid * 16 + i) & 0xffff];
+  Tw t[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = tw[(tid + i) & 255];
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int lam = 0; lam < 4; ++lam) {
+      const int h = 8 >> lam;
+#pragma unroll
+      for (int g = 0; g < (1 << lam); ++g)
+#pragma unroll
+        for (int r = 0; r < h; ++r) bfly<V>(x[g * 2 * h + r], x[g * 2 * h + r + h], t[lam].w, t[lam].wp);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[(size_t)tid * 16 + i] = x[i];
+}
+
+static u64 mulmod(u64 a, u64 b, u64 p) { return (u64)((unsigned __int128)a * b % p); }
+
+template <int V, int MINB = 2>
+static int run(const char* name, int iters_time, bool check = true) {
+  const u64 P = kP0;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned blocks = sms * 8, threads = 256;
+  const size_t nthreads = (size_t)blocks * threads;
+  std::vector<u64> hin(65536);
+  u64 s = 0x9e3779b97f4a7c15ull;
+  for (auto& v : hin) {
+    s ^= s << 13, s ^= s >> 7, s ^= s << 17;
+    v = s;  // lazy inputs: any u64
+  }
+  // some extreme values
+  hin[0] = 0, hin[1] = ~0ull, hin[2] = P, hin[3] = P - 1, hin[4] = P + 1, hin[5] = 1, hin[16] = ~0ull, hin[17] = ~0ull;
+  std::vector<Tw> htw(256);
+  const u64 pinv = montgomery_inverse(P);
+  for (int i = 0; i < 256; ++i) {
+    s ^= s << 13, s ^= s >> 7, s ^= s << 17;
+    u64 w = s % P;
+    if (i == 0) w = P - 1;
+    if (i == 1) w = 1;
+    if (i == 2) w = 0;
+    htw[i].w = w;
+    htw[i].wp = w * pinv;
+  }
+  u64 *din, *dout;
+  Tw* dtw;
+  cudaMalloc(&din, 65536 * 8);
+  cudaMalloc(&dout, nthreads * 16 * 8);
+  cudaMalloc(&dtw, 256 * sizeof(Tw));
+  cudaMemcpy(din, hin.data(), 65536 * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(dtw, htw.data(), 256 * sizeof(Tw), cudaMemcpyHostToDevice);
+  // correctness: 2 iterations, compare residues mod P for the first 4096 threads
+  loop_kernel<V, MINB><<<blocks, threads>>>(dout, din, dtw, 2);
+  cudaDeviceSynchronize();
+  std::vector<u64> got(4096 * 16);
+  cudaMemcpy(got.data(), dout, got.size() * 8, cudaMemcpyDeviceToHost);
+  // 2^-64 mod P
+  u64 rinv = 1;
+  {
+    // R^-1 = (2^64 mod P)^(P-2)
+    u64 base = (u64)((((unsigned __int128)1) << 64) % P), e = P - 2;
+    while (e) {
+      if (e & 1) rinv = mulmod(rinv, base, P);
+      base = mulmod(base, base, P);
+      e >>= 1;
+    }
+  }
+  size_t bad = 0;
+  for (u32 tid = 0; tid < 4096; ++tid) {
+    u64 x[16];
+    for (int i = 0; i < 16; ++i) x[i] = hin[(tid * 16 + i) & 0xffff] % P;
+    for (int it = 0; it < 2; ++it)
+      for (int lam = 0; lam < 4; ++lam) {
+        const int h = 8 >> lam;
+        const u64 om = mulmod(htw[(tid + lam) & 255].w, rinv, P);
+        for (int g = 0; g < (1 << lam); ++g)
+          for (int r = 0; r < h; ++r) {
+            u64 &a = x[g * 2 * h + r], &b = x[g * 2 * h + r + h];
+            const u64 u = mulmod(b, om, P);
+            const u64 s0 = (u64)(((unsigned __int128)a + u) % P), d0 = (u64)(((unsigned __int128)a + P - u) % P);
+            a = s0, b = d0;
+          }
+      }
+    for (int i = 0; i < 16; ++i)
+      if (check && got[(size_t)tid * 16 + i] % P != x[i]) ++bad;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    loop_kernel<V, MINB><<<blocks, threads>>>(dout, din, dtw, iters_time);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep && ms < best) best = ms;
+  }
+  const double bf = 32.0 * iters_time * nthreads;
+  int clk = 0;
+  cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
+  const double cyc = best * 1e-3 * clk * 1e3 * sms * 4 / (bf / 32);
+  printf("{\"variant\": \"%s\", \"minb\": %d, \"bad\": %zu, \"ms\": %.3f, \"gbfly_s\": %.1f, \"cyc_per_warp_bfly_at_maxclk\": %.1f}\n", name, MINB, bad,
+         best, bf / (best * 1e-3) / 1e9, cyc);
+  fflush(stdout);
+  cudaFree(din), cudaFree(dout), cudaFree(dtw);
+  return bad != 0;
+}
+
+int main(int argc, char** argv) {
+  const int iters = argc > 1 ? atoi(argv[1]) : 500;
+  int rc = 0;
+  rc |= run<9, 2>("v9_field_cuh_now", iters);
+  rc |= run<10, 2>("v10_one_alu_fix", iters);
+  rc |= run<11, 2>("v11_two_alu_fix", iters);
+  return rc;
+}
