@@ -51,6 +51,9 @@ cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st)
 template <class F, int LOGN, bool COL, bool INV, bool MAP = false>
 cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
   if constexpr (!COL) {
+    if constexpr (!INV && !MAP) {
+      if (prm.pointwise != nullptr) return launch_kernel<F, LOGN, COL, INV, MAP, kPointwise>(prm, grid, st);
+    }
     return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
   } else if constexpr (MAP) {
     if (prm.twist_full != nullptr) return cudaErrorInvalidValue;

@@ -36,7 +36,9 @@
 
 namespace xntt {
 
-enum TwistKind { kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2 };
+// what the last forward / first inverse stage fuses besides the butterflies (a template parameter: tested at run
+// time, either costs the plain path 3-4 %)
+enum TwistKind { kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2, kPointwise = 3 };
 
 template <int LOGN>
 struct Stages {
@@ -399,6 +401,26 @@ __device__ __forceinline__ void inv_network(const F& f, u64 (&x)[1 << LOGR][C], 
   }
 }
 
+// Barrier between two adjacent radix-8 stages.  Their exchange is closed over blocks of 8 * 2^LOGS consecutive k
+// (LOGS = the smaller of the two strides), and in both stages the tasks of one block sit on the same GT
+// consecutive threads (GT = 2^LOGS, times the column groups in column mode) in the same loop iteration - so only
+// those threads have to meet: a warp-level barrier for the innermost exchange, a named barrier for the next one.
+template <int GT>
+__device__ __forceinline__ void stage_barrier() {
+#if !defined(XNTT_HOST_EMU)
+  if constexpr (GT <= 32) {
+    __syncwarp();
+  } else if constexpr (GT < kThreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.x / GT), "n"(GT) : "memory");
+  } else {
+    __syncthreads();
+  }
+#endif
+}
+#ifndef XNTT_GROUP_BARRIERS
+#define XNTT_GROUP_BARRIERS 1
+#endif
+
 // ---------------------------------------------------------------------------------------------
 template <class F, class Cfg, int TWIST, int J>
 __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
@@ -432,27 +454,40 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
       smem_load<Cfg, R>(sm, k0, LOGS, p, x);
     fwd_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, B);
     if constexpr (J == NS - 1) {
-      if constexpr (TWIST != kNoTwist) apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
+      if constexpr (TWIST == kCompactTwist || TWIST == kFullTwist) {
+        apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
+      } else if constexpr (TWIST == kPointwise) {
+        // fused point-wise product of a polynomial multiply
+        // (examples/magic-series/gaussian-polynomial.hpp:201-212); the Montgomery product is canonical
+        u64 b[R][Cfg::C];
 #pragma unroll
-      for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int c = 0; c < Cfg::C; ++c) {
-          if constexpr (TWIST != kNoTwist) {
-          } else if (prm.pointwise != nullptr) {
-            // fused point-wise product of a polynomial multiply
-            // (examples/magic-series/gaussian-polynomial.hpp:201-212); the Montgomery product is canonical
-            const u64 b = (prm.pointwise + (gdst - prm.dst))[gofs<Cfg>(prm, prm.dmap, k0 + (r << LOGS), p, c)];
-            x[r][c] = f.mont(x[r][c], b, f.companion(b));
-          } else {
-            x[r][c] = f.canon(x[r][c]);
+          for (int c = 0; c < Cfg::C; ++c) {
+            // rows past the end of a ragged last tile hold nothing to multiply with
+            const bool ok = Cfg::COL || row0 + (u32)(p * Cfg::C + c) < prm.rows;
+            b[r][c] = ok ? (prm.pointwise + (gdst - prm.dst))[gofs<Cfg>(prm, prm.dmap, k0 + (r << LOGS), p, c)] : 0ull;
           }
-        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], b[r][c], f.companion(b[r][c]));
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.canon(x[r][c]);
+      }
       gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
     } else {
       smem_store<Cfg, R>(sm, k0, LOGS, p, x);
     }
   }
-  if constexpr (J != NS - 1) __syncthreads();
+  if constexpr (J != NS - 1) {
+    constexpr bool kBothRadix8 = (J >= 1 || Cfg::LOGR1 == 3) && NTASK >= kThreads;
+    constexpr int GT = (XNTT_GROUP_BARRIERS && kBothRadix8 && LOGS <= 8) ? (1 << LOGS) * (Cfg::COL ? Cfg::NP : 1) : kThreads;
+    stage_barrier<(GT < kThreads ? GT : kThreads)>();
+  }
 }
 
 template <class F, class Cfg, int TWIST, int J>
@@ -481,7 +516,8 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
     u64 x[R][Cfg::C];
     if constexpr (J == 0) {
       gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
-      if constexpr (TWIST != kNoTwist) apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
+      if constexpr (TWIST == kCompactTwist || TWIST == kFullTwist)
+        apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
     } else {
       smem_load<Cfg, R>(sm, k0, LOGS, p, x);
     }
@@ -503,7 +539,12 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
       smem_store<Cfg, R>(sm, k0, LOGS, p, x);
     }
   }
-  if constexpr (J != NS - 1) __syncthreads();
+  if constexpr (J != NS - 1) {
+    // the next stage (stride 2^(LOGS + 3)) is radix 8 unless it is the last one of a length that is not 8^k
+    constexpr bool kBothRadix8 = (J + 1 < NS - 1 || Cfg::LOGR1 == 3) && NTASK >= kThreads;
+    constexpr int GT = (XNTT_GROUP_BARRIERS && kBothRadix8 && LOGS + 3 <= 8) ? (1 << (LOGS + 3)) * (Cfg::COL ? Cfg::NP : 1) : kThreads;
+    stage_barrier<(GT < kThreads ? GT : kThreads)>();
+  }
 }
 
 template <class F, class Cfg, bool INVERSE, int TWIST, int... Js>

@@ -74,7 +74,10 @@ static int emu_launch2(const PassParams& prm, unsigned grid) {
     // poison shared memory so that a missing write shows up
     memset(sm.data(), 0xcd, sm.size() * sizeof(sm[0]));
     // same choice of the twist form as dispatch.cuh: launch_one
-    if (!COL)
+    if (!COL && !INV && !MAP && prm.pointwise != nullptr)
+      emu_stages<F, Cfg, INV, kPointwise>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
+                                          std::make_integer_sequence<int, Cfg::NS>{});
+    else if (!COL)
       emu_stages<F, Cfg, INV, kNoTwist>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
                                         std::make_integer_sequence<int, Cfg::NS>{});
     else if (prm.twist_full != nullptr && !MAP)

@@ -64,6 +64,12 @@ for path in libs:
         fb, _ = timeit(lambda: plan.forward(dst.data_ptr(), src.data_ptr(), st))
         ib, _ = timeit(lambda: plan.inverse(dst.data_ptr(), src.data_ptr(), st))
         key = f"2^{L}x{batch}{plan.splits}"
+        per = []
+        for i in range(len(plan.splits)):
+            tf, _ = timeit(lambda: plan.run_pass(i, 0, dst.data_ptr(), src.data_ptr(), st), reps=15)
+            ti, _ = timeit(lambda: plan.run_pass(i, 1, dst.data_ptr(), src.data_ptr(), st), reps=15)
+            per.append((round(tf * 1e3, 1), round(ti * 1e3, 1)))
+        print(f"{name:10s} {key:26s} per-pass (fwd, inv) us: {per}", flush=True)
         res[name][key] = [round(fb * 1e3, 1), round(ib * 1e3, 1), round(m * batch / fb / 1e6, 1)]
         print(f"{name:10s} parity={ok} {key:26s} fwd {fb*1e3:9.1f} us inv {ib*1e3:9.1f} us  {m*batch/fb/1e6:6.1f} Gelem/s fwd",
               flush=True)

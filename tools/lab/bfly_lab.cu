@@ -165,8 +165,9 @@ static int run(const char* name, int iters_time, bool check = true) {
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 500;
   int rc = 0;
-  rc |= run<9, 2>("v9_field_cuh_now", iters);
-  rc |= run<10, 2>("v10_one_alu_fix", iters);
-  rc |= run<11, 2>("v11_two_alu_fix", iters);
+  const int only = argc > 2 ? atoi(argv[2]) : -1;
+  if (only < 0 || only == 9) rc |= run<9, 2>("v9_field_cuh_now", iters);
+  if (only < 0 || only == 6) rc |= run<6, 2>("v6_probe_nofix", iters, false);
+  if (only < 0 || only == 7) rc |= run<7, 2>("v7_probe_mont_only", iters, false);
   return rc;
 }
