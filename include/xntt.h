@@ -168,6 +168,17 @@ int xntt_multiply_normalize(const xntt_plan* plan, uint64_t* dst, const uint64_t
 int xntt_transpose(uint64_t* dst, const uint64_t* src, uint64_t rows, uint64_t cols, uint64_t ld_dst, uint64_t ld_src,
                    void* stream);
 
+/* Kinnaes' formula for the number of magic series modulo `modulus` - the reference's second example
+ * (examples/magic-series-kinnaes/kinnaes.hpp), a pure PAdic64 multiply workload at a root of unity of odd order:
+ *   xntt_kinnaes_sum     : MagicSeriesKinnaes<m, PAdic64<Modulus<modulus, generator>>, n>::compute_sum(j_begin, j_end)
+ *                          (kinnaes.hpp:51-157), 0 <= j_begin <= j_end <= n / 2
+ *   xntt_kinnaes_compute : ...::compute() (kinnaes.hpp:27-34) = (2 compute_sum(0, n / 2) + binomial(m^2, m)) / n
+ * n must divide modulus - 1 (else XNTT_ERR_INVALID, like Modulus::get_root_forward), 2 <= m < 2^20.
+ * device = CUDA ordinal, -1 = current.  The result is a canonical residue. */
+int xntt_kinnaes_sum(uint64_t modulus, uint64_t generator, uint64_t m, uint64_t n, uint64_t j_begin, uint64_t j_end,
+                     int device, uint64_t* result);
+int xntt_kinnaes_compute(uint64_t modulus, uint64_t generator, uint64_t m, uint64_t n, int device, uint64_t* result);
+
 /* Device-resident PageMemory twin (include/sventt/vector.hpp:61-168): pinned host memory for the
  * host entry points / device memory for the device ones. */
 int xntt_alloc_device(void** ptr, size_t bytes, int device);

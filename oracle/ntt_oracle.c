@@ -168,3 +168,49 @@ uint64_t oracle_fnv64(const uint64_t* v, uint64_t count) {
   for (uint64_t i = 0; i < count; ++i) h = (h ^ v[i]) * 0x100000001b3ull;
   return h;
 }
+
+/* ---- Kinnaes' formula for the number of magic series (examples/magic-series-kinnaes/kinnaes.hpp) ----
+ *
+ * x / y mod N  (sventt::Modulus::divide, include/sventt/modulus.hpp; N prime: Fermat inverse) */
+static uint64_t divmod(uint64_t x, uint64_t y, uint64_t N) { return oracle_mulmod(x % N, oracle_powmod(y % N, N - 2, N), N); }
+
+/* MagicSeriesKinnaes::compute_comb(a, b) = binomial(a, b) mod N  (kinnaes.hpp:36-47) */
+uint64_t oracle_kinnaes_comb(uint64_t a, uint64_t b, uint64_t N) {
+  uint64_t num = a % N, den = b % N;
+  for (uint64_t i = 1; i < b; ++i) num = oracle_mulmod(num, (a - i) % N, N);
+  for (uint64_t i = 2; i < b; ++i) den = oracle_mulmod(den, i % N, N);
+  return divmod(num, den, N);
+}
+
+/* MagicSeriesKinnaes::compute_sum(j_begin, j_end)  (kinnaes.hpp:51-157), lane by lane:
+ *   sum over J = j_begin+1 .. j_end of  prod_{l<m} (w^(J (m^2-m+1+l)) - 1)  /  ( w^(J r) prod_{l<m} (w^(J (l+1)) - 1) )
+ * with w a primitive n-th root of unity and r = m (m-1)/2 * m; accumulated as one fraction like the
+ * reference does (kinnaes.hpp:126-133) and divided at the end (:156).  Returns 0 when n does not divide N-1. */
+uint64_t oracle_kinnaes_sum(uint64_t N, uint64_t g, uint64_t m, uint64_t n, uint64_t j_begin, uint64_t j_end) {
+  const uint64_t w = oracle_root_forward(N, g, n);
+  if (w == 0) return 0;
+  const uint64_t r = m * (m - 1) / 2 * m;
+  uint64_t num_sum = 0, den_sum = 1;
+  for (uint64_t J = j_begin + 1; J <= j_end; ++J) {
+    const uint64_t wj = oracle_powmod(w, J, N);
+    uint64_t num_term = oracle_powmod(wj, m * m - m + 1, N), den_term = wj;
+    uint64_t num_prod = 1, den_prod = oracle_powmod(wj, r, N);
+    for (uint64_t l = 0; l < m; ++l) {
+      num_prod = oracle_mulmod(submod(num_term, 1, N), num_prod, N);
+      den_prod = oracle_mulmod(submod(den_term, 1, N), den_prod, N);
+      num_term = oracle_mulmod(num_term, wj, N);
+      den_term = oracle_mulmod(den_term, wj, N);
+    }
+    num_sum = addmod(oracle_mulmod(den_sum, num_prod, N), oracle_mulmod(num_sum, den_prod, N), N);
+    den_sum = oracle_mulmod(den_sum, den_prod, N);
+  }
+  return divmod(num_sum, den_sum, N);
+}
+
+/* MagicSeriesKinnaes::compute()  (kinnaes.hpp:27-34): (2 * compute_sum(0, n/2) + binomial(m^2, m)) / n */
+uint64_t oracle_kinnaes_compute(uint64_t N, uint64_t g, uint64_t m, uint64_t n) {
+  uint64_t sum = oracle_kinnaes_sum(N, g, m, n, 0, n / 2);
+  sum = addmod(sum, sum, N);
+  sum = addmod(sum, oracle_kinnaes_comb(m * m, m, N), N);
+  return divmod(sum, n, N);
+}

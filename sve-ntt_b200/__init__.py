@@ -85,6 +85,9 @@ SYMBOLS = {
     "xntt_last_cuda_error": (C.c_char_p, []),
     "xntt_version": (C.c_char_p, []),
     "xntt_device_count": (C.c_int, []),
+    "xntt_kinnaes_sum": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
+                                 C.POINTER(C.c_uint64)]),
+    "xntt_kinnaes_compute": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "xntt_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -124,6 +127,18 @@ class Library:
     def transpose(self, dst, src, rows, cols, ld_dst=None, ld_src=None, stream=0):
         self.check(self.lib.xntt_transpose(dst, src, rows, cols, rows if ld_dst is None else ld_dst,
                                            cols if ld_src is None else ld_src, stream), "xntt_transpose")
+
+    # MagicSeriesKinnaes<m, PAdic64<Modulus<modulus, generator>>, n> (examples/magic-series-kinnaes/kinnaes.hpp)
+    def kinnaes_sum(self, modulus, generator, m, n, j_begin, j_end, device=-1):
+        r = C.c_uint64()
+        self.check(self.lib.xntt_kinnaes_sum(modulus, generator, m, n, j_begin, j_end, device, C.byref(r)),
+                   "xntt_kinnaes_sum")
+        return int(r.value)
+
+    def kinnaes_compute(self, modulus, generator, m, n, device=-1):
+        r = C.c_uint64()
+        self.check(self.lib.xntt_kinnaes_compute(modulus, generator, m, n, device, C.byref(r)), "xntt_kinnaes_compute")
+        return int(r.value)
 
     def microbench(self, kind, iters):
         g, ms = C.c_double(), C.c_double()

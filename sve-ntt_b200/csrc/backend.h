@@ -35,6 +35,8 @@ int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, 
 // dst[ld_dst * c + r] = src[ld_src * r + c]; dst == src with rows == cols and equal leading dimensions
 // is the in-place square form
 int launch_transpose(u64* dst, const u64* src, u64 rows, u64 cols, u64 ld_dst, u64 ld_src, void* stream);
+// Kinnaes sum: fills prm.partial[0 .. 2 * blocks) (device memory) with one Montgomery-form fraction per CTA
+int launch_kinnaes(const KinnaesParams& prm, unsigned blocks, void* stream);
 int microbench(int kind, int iters, double* gops, double* ms);
 
 }  // namespace be

@@ -8,6 +8,7 @@
 
 #include "backend.h"
 #include "dispatch.cuh"
+#include "kinnaes_kernel.cuh"
 #include "misc_kernels.cuh"
 #include "transpose_kernel.cuh"
 
@@ -251,6 +252,12 @@ int launch_gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int lo
   const u32 threads = 128, blocks = (count + threads - 1) / threads;
   XNTT_WITH_FIELD(fc, (gen_table_kernel<F><<<blocks, threads, 0, (cudaStream_t)stream>>>(f, out, count, kind, logn,
                                                                                        shift, t)));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int launch_kinnaes(const KinnaesParams& prm, unsigned blocks, void* stream) {
+  XNTT_WITH_FIELD(prm.field, (kinnaes_kernel<F><<<blocks, kKinnaesThreads, 0, (cudaStream_t)stream>>>(f, prm)));
   CU(cudaGetLastError());
   return 0;
 }

@@ -86,6 +86,22 @@ struct PowTable {
   u64 sq[32];  // root^(2^i) in Montgomery form
   u64 scale;   // Montgomery form of the extra factor (2^64 mod P for none)
 };
+// Kinnaes sum (kinnaes_kernel.cuh)
+constexpr int kKinnaesThreads = 256;
+constexpr int kKinnaesLadder = 40;
+constexpr unsigned kKinnaesMaxBlocks = 148 * 8;  // one resident wave of 256-thread CTAs
+
+struct KinnaesParams {
+  FieldConsts field;
+  u64 m;          // order of the magic series
+  u64 j_first;    // first J (= j_begin + 1)
+  u64 count;      // number of consecutive J
+  u64 exp_num;    // m^2 - m + 1
+  u64 exp_r;      // r = m (m-1)/2 * m
+  u64 ladder[kKinnaesLadder];  // w^(2^i) in Montgomery form
+  u64* partial;   // out: [2 * gridDim.x] (numerator, denominator) per CTA, Montgomery form
+};
+
 enum TableKind { kFwdG = 0, kInvI = 1, kPowers = 2, kTwist = 3 };
 
 }  // namespace xntt

@@ -417,6 +417,10 @@ __device__ __forceinline__ void stage_barrier() {
   }
 #endif
 }
+#ifndef XNTT_TASK_UNROLL
+#define XNTT_TASK_UNROLL 1
+#endif
+constexpr int kTaskUnroll = XNTT_TASK_UNROLL;  // tasks of one stage a thread works on at a time
 #ifndef XNTT_GROUP_BARRIERS
 #define XNTT_GROUP_BARRIERS 1
 #endif
@@ -435,7 +439,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
 #if XNTT_PREFETCH_TW
   if constexpr (J + 1 < NS) prefetch_fwd_stage<Cfg, J + 1>(prm.tw);
 #endif
-#pragma unroll 1
+#pragma unroll(kTaskUnroll)
   for (int task = threadIdx.x; task < NTASK; task += kThreads) {
     int p, t;
     if constexpr (Cfg::COL) {
@@ -501,7 +505,7 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
   constexpr int LOGS = 3 * J;
   constexpr int LOGT = Cfg::LOGN - LOGR;
   constexpr int NTASK = (1 << LOGT) * Cfg::NP;
-#pragma unroll 1
+#pragma unroll(kTaskUnroll)
   for (int task = threadIdx.x; task < NTASK; task += kThreads) {
     int p, t;
     if constexpr (Cfg::COL) {

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -818,6 +819,88 @@ int xntt_device_count(void) {
   const int rc = be::device_count(&n);
   if (rc != 0) return be_fail(rc);
   return n;
+}
+
+// ---- Kinnaes' formula (examples/magic-series-kinnaes/kinnaes.hpp) --------------------------------------------
+namespace {
+int kinnaes_sum_impl(u64 p, u64 gen, u64 m, u64 n, u64 j_begin, u64 j_end, int device, u64* result) {
+  if ((p & 1) == 0 || p < 3 || gen == 0 || !h_is_prime(p)) return XNTT_ERR_INVALID;
+  if (m < 2 || m >= (1ull << 20) || n == 0 || (p - 1) % n != 0) return XNTT_ERR_INVALID;
+  if (j_begin > j_end || j_end > n / 2) return XNTT_ERR_INVALID;
+  *result = 0;
+  if (j_begin == j_end) return XNTT_OK;  // empty sum: 0 / 1
+  int dev = device;
+  if (dev < 0) BE(be::get_device(&dev));
+  DeviceGuard g(dev);
+  if (!g.ok) return be_fail(1);
+  KinnaesParams prm{};
+  prm.field.p = p;
+  prm.field.pinv = h_montgomery_inverse(p);
+  prm.field.one = h_to_mont(1, p);
+  prm.m = m;
+  prm.j_first = j_begin + 1;
+  prm.count = j_end - j_begin;
+  prm.exp_num = m * m - m + 1;
+  prm.exp_r = m * (m - 1) / 2 * m;
+  u64 w = h_pow(gen % p, (p - 1) / n, p);  // Modulus::get_root_forward(n)
+  for (int i = 0; i < kKinnaesLadder; ++i) {
+    prm.ladder[i] = h_to_mont(w, p);
+    w = h_mul(w, w, p);
+  }
+  u64 blocks = (prm.count + kKinnaesThreads - 1) / kKinnaesThreads;
+  if (blocks > kKinnaesMaxBlocks) blocks = kKinnaesMaxBlocks;
+  // one small result buffer per device, kept for the life of the process (a cudaMalloc / cudaFree pair per call
+  // costs 5-7 ms, thirty times the kernel); calls are serialised on it
+  static std::mutex mu;
+  static void* scratch[64] = {};
+  if (dev >= 64) return XNTT_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!scratch[dev]) BE(be::dev_malloc(&scratch[dev], kKinnaesMaxBlocks * 2 * sizeof(u64)));
+  void* dpart = scratch[dev];
+  prm.partial = static_cast<u64*>(dpart);
+  std::vector<u64> part(blocks * 2);
+  int rc = XNTT_OK, brc;
+  if ((brc = be::launch_kinnaes(prm, (unsigned)blocks, nullptr)) != 0) rc = be_fail(brc);
+  if (rc == XNTT_OK && (brc = be::memcpy_d2h(part.data(), dpart, part.size() * sizeof(u64), nullptr)) != 0) rc = be_fail(brc);
+  if (rc == XNTT_OK && (brc = be::stream_sync(nullptr)) != 0) rc = be_fail(brc);
+  if (rc != XNTT_OK) return rc;
+  // fold the per-CTA fractions and divide once (kinnaes.hpp:143-156); from Montgomery form: x * 2^-64
+  const u64 rinv = h_inv(h_to_mont(1, p), p);
+  u64 num = 0, den = 1;
+  for (u64 b = 0; b < blocks; ++b) {
+    const u64 nb = h_mul(part[2 * b], rinv, p), db = h_mul(part[2 * b + 1], rinv, p);
+    num = (u64)(((u128)h_mul(den, nb, p) + h_mul(num, db, p)) % p);
+    den = h_mul(den, db, p);
+  }
+  if (den == 0) return XNTT_ERR_INVALID;  // n is not the order of a usable root for this m
+  *result = h_mul(num, h_inv(den, p), p);
+  return XNTT_OK;
+}
+}  // namespace
+
+int xntt_kinnaes_sum(uint64_t modulus, uint64_t generator, uint64_t m, uint64_t n, uint64_t j_begin, uint64_t j_end,
+                     int device, uint64_t* result) {
+  u64 r = 0;
+  const int rc = kinnaes_sum_impl(modulus, generator, m, n, j_begin, j_end, device, &r);
+  if (result) *result = r;
+  return result ? rc : XNTT_ERR_INVALID;
+}
+
+int xntt_kinnaes_compute(uint64_t modulus, uint64_t generator, uint64_t m, uint64_t n, int device, uint64_t* result) {
+  if (!result) return XNTT_ERR_INVALID;
+  u64 sum = 0;
+  const int rc = kinnaes_sum_impl(modulus, generator, m, n, 0, n / 2, device, &sum);
+  if (rc != XNTT_OK) return rc;
+  const u64 p = modulus;
+  sum = (u64)(((u128)sum + sum) % p);
+  // compute_comb(m * m, m) (kinnaes.hpp:36-47)
+  const u64 a = m * m;
+  u64 num = a % p, den = m % p;
+  for (u64 i = 1; i < m; ++i) num = h_mul(num, (a - i) % p, p);
+  for (u64 i = 2; i < m; ++i) den = h_mul(den, i % p, p);
+  sum = (u64)(((u128)sum + h_mul(num, h_inv(den, p), p)) % p);
+  *result = h_mul(sum, h_inv(n % p, p), p);
+  return XNTT_OK;
 }
 
 int xntt_microbench(int kind, int iters, double* gops, double* ms) {

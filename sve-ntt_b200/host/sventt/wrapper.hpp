@@ -55,7 +55,8 @@ class NTT {
     d.log2_m = detail::log2_exact(get_m());
     d.batch = batch;
     d.inverse_factor = kernel_type::get_inverse_factor();
-    d.flags = (enable_forward ? XNTT_ENABLE_FORWARD : 0u) | (enable_inverse ? XNTT_ENABLE_INVERSE : 0u);
+    d.flags = (enable_forward ? static_cast<std::uint32_t>(XNTT_ENABLE_FORWARD) : 0u) |
+              (enable_inverse ? static_cast<std::uint32_t>(XNTT_ENABLE_INVERSE) : 0u);
     if (d.flags == 0) d.flags = XNTT_ENABLE_FORWARD | XNTT_ENABLE_INVERSE;
     d.device = device;
     std::vector<std::uint32_t> splits;

@@ -36,6 +36,7 @@ static inline unsigned __brev(unsigned v) {
 #define __grid_constant__
 
 #include "../../sve-ntt_b200/csrc/backend.h"
+#include "../../sve-ntt_b200/csrc/kinnaes_kernel.cuh"
 #include "../../sve-ntt_b200/csrc/misc_kernels.cuh"
 #include "../../sve-ntt_b200/csrc/pass_kernel.cuh"
 #include "../../sve-ntt_b200/csrc/transpose_kernel.cuh"
@@ -180,6 +181,25 @@ int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& pr
 int launch_gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, const PowTable& t,
                      void*) {
   EMU_WITH_FIELD(fc, for (u32 i = 0; i < count; ++i) out[i] = table_entry<F>(f, i, kind, logn, shift, t));
+  return 0;
+}
+template <class F>
+static void emu_kinnaes(const F& f, const KinnaesParams& prm, unsigned blocks) {
+  // same device functions, CTA by CTA; the fractions of a CTA are folded one after the other instead of in a tree
+  for (unsigned b = 0; b < blocks; ++b) {
+    u64 ns = 0, ds = f.one();
+    for (unsigned t = 0; t < (unsigned)kKinnaesThreads; ++t)
+      for (u64 i = (u64)b * kKinnaesThreads + t; i < prm.count; i += (u64)blocks * kKinnaesThreads) {
+        u64 n, d;
+        kinnaes_term<F>(f, prm, prm.j_first + i, n, d);
+        kinnaes_fold<F>(f, ns, ds, n, d);
+      }
+    prm.partial[2 * b] = ns;
+    prm.partial[2 * b + 1] = ds;
+  }
+}
+int launch_kinnaes(const KinnaesParams& prm, unsigned blocks, void*) {
+  EMU_WITH_FIELD(prm.field, emu_kinnaes<F>(f, prm, blocks));
   return 0;
 }
 int launch_to_mont(const FieldConsts& fc, u64* dst, const u64* src, size_t n, u64 r2, void*) {

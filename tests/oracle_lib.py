@@ -17,7 +17,8 @@ _ptr = C.c_void_p
 
 
 def _build_oracle():
-    if not os.path.exists(ORACLE_SO):
+    src = os.path.join(ORACLE_DIR, "ntt_oracle.c")
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
         subprocess.run(["make", "_build/libntt_oracle.so"], cwd=ORACLE_DIR, check=True)
 
 
@@ -48,6 +49,9 @@ class Oracle:
             ("oracle_dft_point", _u64, [_ptr, _u64, _u64, _u64, _u64]),
             ("oracle_fill_xorshift", None, [_ptr, _u64, _u64, _u64]),
             ("oracle_fnv64", _u64, [_ptr, _u64]),
+            ("oracle_kinnaes_comb", _u64, [_u64, _u64, _u64]),
+            ("oracle_kinnaes_sum", _u64, [_u64, _u64, _u64, _u64, _u64, _u64]),
+            ("oracle_kinnaes_compute", _u64, [_u64, _u64, _u64, _u64]),
         ]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
@@ -74,6 +78,12 @@ class Oracle:
         out = np.empty(count, dtype=np.uint64)
         self.lib.oracle_fill_xorshift(_p(out), count, seed, N)
         return out
+
+    def kinnaes_sum(self, N, g, m, n, j_begin, j_end):
+        return int(self.lib.oracle_kinnaes_sum(N, g, m, n, j_begin, j_end))
+
+    def kinnaes_compute(self, N, g, m, n):
+        return int(self.lib.oracle_kinnaes_compute(N, g, m, n))
 
     def fnv64(self, a):
         return int(self.lib.oracle_fnv64(_p(a), a.size))

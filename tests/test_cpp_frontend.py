@@ -32,3 +32,17 @@ def test_reference_compositions_on_gpu():
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ALL OK" in out.stdout and "MISMATCH" not in out.stdout
     assert out.stdout.count(" ok") == 20
+
+
+def test_kinnaes_class_on_emulator():
+    """MagicSeriesKinnaes<m, PAdic64SVE<Modulus<N, g>>, n> (examples/magic-series-kinnaes) through the C++ drop-in."""
+    exe = _build("kinnaes_tests_emu")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 2, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_kinnaes_class_on_gpu():
+    exe = _build("kinnaes_tests_gpu")
+    out = subprocess.run([exe, "--all"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 12, out.stdout + out.stderr

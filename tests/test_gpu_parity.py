@@ -204,6 +204,37 @@ def test_host_entry_points(cuda_lib, oracle):
     plan.close()
 
 
+@pytest.mark.parametrize("L,batch", [(16, 1), (12, 5), (20, 2), (9, 3)])
+def test_host_entry_points_page_locked(cuda_lib, oracle, L, batch):
+    """Page-locked host buffers (what bench.py's e2e leg and sventt::PageMemory hand in): same words as the
+    pageable route, also in place, batched and for single-pass plans."""
+    import torch
+    m = 1 << L
+    a = oracle.fill_xorshift(m * batch, SEED + L, P0)
+    want = np.concatenate([oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), P0, G0) for b in range(batch)])
+    plan = cuda_lib.plan(L, batch=batch)
+    src = torch.from_numpy(a.view(np.int64)).pin_memory()
+    dst = torch.empty_like(src).pin_memory()
+    plan.forward_host(dst.data_ptr(), src.data_ptr())
+    assert np.array_equal(dst.numpy().view(np.uint64), want)
+    assert np.array_equal(src.numpy().view(np.uint64), a)  # out of place keeps the source
+    back = torch.empty_like(src).pin_memory()
+    plan.inverse_host(back.data_ptr(), dst.data_ptr())
+    assert np.array_equal(back.numpy().view(np.uint64), a)
+    # in place, page-locked
+    plan.forward_host(src.data_ptr(), src.data_ptr())
+    assert np.array_equal(src.numpy().view(np.uint64), want)
+    plan.inverse_host(src.data_ptr(), src.data_ptr())
+    assert np.array_equal(src.numpy().view(np.uint64), a)
+    # mixed: page-locked source, pageable destination and the other way round
+    out = np.empty_like(a)
+    plan.forward_host(out.ctypes.data, src.data_ptr())
+    assert np.array_equal(out, want)
+    plan.inverse_host(back.data_ptr(), out.ctypes.data)
+    assert np.array_equal(back.numpy().view(np.uint64), a)
+    plan.close()
+
+
 def test_full_size_2p24(cuda_lib, oracle):
     """BASELINE configs[1]: n = 2^24 on one GPU, word for word against the oracle, plus round trip,
     linearity and directly evaluated output words."""
