@@ -46,21 +46,27 @@ cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st)
   return cudaGetLastError();
 }
 
-// Column passes carry the six-step twiddle in one of two forms (pass_kernel.cuh: apply_twist); the generalised-
-// addressing kernels of sharded plans only exist in the compact form (the planner never gives them a full matrix).
+// one instantiation per kind a pass can take (pass_kernel.cuh: pass_kind); the generalised-addressing kernels of
+// sharded plans only exist in the compact / plain forms (the planner never gives them a matrix)
 template <class F, int LOGN, bool COL, bool INV, bool MAP = false>
 cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
-  if constexpr (!COL) {
+  const int kind = pass_kind(COL, INV, MAP, prm);
+  if constexpr (COL) {
+    if (kind == kCompactTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist>(prm, grid, st);
+    if constexpr (!MAP) {
+      if (kind == kFullTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kFullTwist>(prm, grid, st);
+      if constexpr (!INV) {
+        if (kind == kNoTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
+      }
+    }
+    return cudaErrorInvalidValue;
+  } else {
     if constexpr (!INV && !MAP) {
-      if (prm.pointwise != nullptr) return launch_kernel<F, LOGN, COL, INV, MAP, kPointwise>(prm, grid, st);
+      if (kind == kPointwise) return launch_kernel<F, LOGN, COL, INV, MAP, kPointwise>(prm, grid, st);
+      if (kind == kPreTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kPreTwist>(prm, grid, st);
+      if (kind == kPrePointwise) return launch_kernel<F, LOGN, COL, INV, MAP, kPrePointwise>(prm, grid, st);
     }
     return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
-  } else if constexpr (MAP) {
-    if (prm.twist_full != nullptr) return cudaErrorInvalidValue;
-    return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist>(prm, grid, st);
-  } else {
-    if (prm.twist_full != nullptr) return launch_kernel<F, LOGN, COL, INV, MAP, kFullTwist>(prm, grid, st);
-    return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist>(prm, grid, st);
   }
 }
 

@@ -64,6 +64,9 @@ struct PassParams {
   u64 inner;           // column mode: elements between consecutive k; row mode: unused
   u64 outer_stride;    // column mode: elements between consecutive outer blocks (= N * inner)
   u32 tiles_per_outer; // column mode: inner / W
+  const Tw* pre_twist;   // forward row pass: the twiddle matrix of the column pass before it, applied while the rows are
+                         // loaded (entry ((row & pre_rows_mask) << log2 N) + k); that column pass then runs without
+  u32 pre_rows_mask;
   u32 twist_shift;
   u32 twist_full_shift;  // log2 of the number of columns of twist_full
   u32 twist_col0;      // column mode: global index of this buffer's first column (sharded plans)

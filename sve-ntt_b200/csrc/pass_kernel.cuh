@@ -36,9 +36,30 @@
 
 namespace xntt {
 
-// what the last forward / first inverse stage fuses besides the butterflies (a template parameter: tested at run
-// time, either costs the plain path 3-4 %)
-enum TwistKind { kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2, kPointwise = 3 };
+// What a pass fuses besides its butterflies - a template parameter (tested at run time, either costs the plain
+// path 3-4 %):
+//   column passes : the six-step twiddle after the last forward / before the first inverse stage, from two
+//                   sqrt(M)-entry tables (kCompactTwist) or from the whole matrix (kFullTwist); kNoTwist when the
+//                   row pass behind it applies the matrix instead
+//   forward rows  : kPreTwist = multiply by the preceding column pass's twiddle matrix while loading (contiguous
+//                   rows of the matrix next to contiguous rows of data, at the start of a tile where the latency
+//                   overlaps the data load - the forward twin of what the inverse column pass does);
+//                   kPointwise = the point-wise product of a polynomial multiply before storing; or both
+enum TwistKind { kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2, kPointwise = 3, kPreTwist = 4, kPrePointwise = 5 };
+
+// the one place that decides (CUDA dispatcher and host emulator both call it)
+inline int pass_kind(bool col, bool inverse, bool map, const PassParams& prm) {
+  if (col) {
+    if (!map && prm.twist_full != nullptr) return kFullTwist;
+    if (prm.twist_lo != nullptr) return kCompactTwist;
+    return kNoTwist;
+  }
+  if (!inverse && !map) {
+    if (prm.pre_twist != nullptr) return prm.pointwise != nullptr ? kPrePointwise : kPreTwist;
+    if (prm.pointwise != nullptr) return kPointwise;
+  }
+  return kNoTwist;
+}
 
 template <int LOGN>
 struct Stages {
@@ -340,6 +361,23 @@ __device__ __forceinline__ void apply_twist(const F& f, const PassParams& prm, u
   }
 }
 
+// forward row pass, stage 0: residue k of row `row` times entry ((row & mask) << LOGN) + k of the matrix
+template <class F, class Cfg, int R>
+__device__ __forceinline__ void apply_pre_twist(const F& f, const PassParams& prm, u64 (&x)[R][Cfg::C], int k0, int logs,
+                                                u32 row) {
+  Tw t[R][Cfg::C];
+#pragma unroll
+  for (int c = 0; c < Cfg::C; ++c) {
+    const Tw* q = prm.pre_twist + ((u64)((row + c) & prm.pre_rows_mask) << Cfg::LOGN);  // the mask keeps ragged tiles in range
+#pragma unroll
+    for (int r = 0; r < R; ++r) t[r][c] = ld_tw_stream(q + (k0 + (r << logs)));
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], t[r][c]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward radix-R register network (Cooley-Tukey, block-indexed twiddles).
 template <class F, int LOGR, int C, bool FIRST>
@@ -452,15 +490,18 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
     const int B = t >> LOGS, i = t & ((1 << LOGS) - 1);
     const int k0 = (B << (LOGS + LOGR)) + i;
     u64 x[R][Cfg::C];
-    if constexpr (J == 0)
+    if constexpr (J == 0) {
       gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
-    else
+      if constexpr (TWIST == kPreTwist || TWIST == kPrePointwise)
+        apply_pre_twist<F, Cfg, R>(f, prm, x, k0, LOGS, row0 + (u32)(p * Cfg::C));
+    } else {
       smem_load<Cfg, R>(sm, k0, LOGS, p, x);
+    }
     fwd_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, B);
     if constexpr (J == NS - 1) {
       if constexpr (TWIST == kCompactTwist || TWIST == kFullTwist) {
         apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
-      } else if constexpr (TWIST == kPointwise) {
+      } else if constexpr (TWIST == kPointwise || TWIST == kPrePointwise) {
         // fused point-wise product of a polynomial multiply
         // (examples/magic-series/gaussian-polynomial.hpp:201-212); the Montgomery product is canonical
         u64 b[R][Cfg::C];

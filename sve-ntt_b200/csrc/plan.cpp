@@ -130,6 +130,13 @@ int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int
   return XNTT_OK;
 }
 
+// Forward only: the twiddle matrix of column pass i is applied by the row pass behind it, while that pass loads
+// its rows (contiguous, next to the data, at the start of a tile) instead of at the end of the column pass's tiles.
+// Holds for the last column pass of an unsharded plan whenever the planner stored its forward matrix.
+bool row_applies_twist(const xntt_plan* pl, size_t i) {
+  return pl->shard_count == 1 && i + 2 == pl->passes.size() && pl->passes[i].fwd_full != nullptr;
+}
+
 // One pass.  `count_override` (when non-zero) replaces the number of outer blocks / rows: the row
 // half of a sharded plan only holds 1/shard_count of them.
 int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* src, void* st,
@@ -156,6 +163,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.twist_shift = (u32)ps.twist_shift;
     prm.twist_full = inverse ? ps.inv_full : ps.fwd_full;
     prm.twist_full_shift = (u32)ps.log_inner;
+    if (!inverse && row_applies_twist(pl, i)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
     prm.twist_col0 = sharded_first ? (u32)(inner * pl->shard_rank) : 0u;
     const u64 tiles = outer * prm.tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -166,6 +174,10 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.rows = (u32)rows;
     prm.scale_on = (inverse && pl->scale_on && pl->passes.size() == 1) ? 1u : 0u;
     prm.pointwise = inverse ? nullptr : pointwise;
+    if (!inverse && i > 0 && row_applies_twist(pl, i - 1)) {
+      prm.pre_twist = pl->passes[i - 1].fwd_full;
+      prm.pre_rows_mask = (1u << pl->passes[i - 1].logn) - 1u;
+    }
     grid = (unsigned)((rows + (1u << logw) - 1) >> logw);
   }
   BE(be::launch_pass(ps.logn, ps.col, inverse, false, prm, grid, st));
@@ -427,13 +439,16 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   size_t words = 0;
   std::vector<size_t> off_fwd(q), off_inv(q), off_flo(q), off_fhi(q), off_ilo(q), off_ihi(q);
   std::vector<size_t> off_ffull(q, 0), off_ifull(q, 0);
-  std::vector<char> use_full(q, 0);
-  // Whole-matrix twiddles: every column pass whose matrix (N * inner entries of 16 bytes per enabled direction)
-  // still fits the budget, outermost first.  Default 128 MiB: matrices that stay L2-resident next to the data
-  // (batched 2^20: +4 %, the inner matrix of 2^28: +2 %); at 2^24 the 256 MiB-per-direction matrix only breaks
-  // even with the compact form (forward 441 vs 430 us, inverse 429 vs 445 us), so it is not worth its memory.
-  // XNTT_TWIST_TABLE_MAX_MB overrides; sharded plans and XNTT_COMPACT_TABLES keep the compact form.
-  size_t full_budget = (size_t)128 << 20;
+  std::vector<char> use_ffull(q, 0), use_ifull(q, 0);
+  // Whole-matrix twiddles (N * inner entries of 16 bytes per pass and direction: one modular product per residue
+  // instead of two, no random table look-ups) while they fit the budget, outermost pass first, inverse before
+  // forward.  The inverse column pass consumes its matrix next to its tile loads; the forward matrix of the last
+  // column pass is consumed by the row pass the same way (row_applies_twist); only the forward matrix of an outer
+  // column pass of a three-pass plan is read at the end of that pass's tiles, which pays off while the matrix
+  // stays L2-resident (<= 64 MiB).  2^24: column pass 228 -> 180 us forward, 241 -> 228 us inverse.
+  // Default budget 512 MiB per plan (both directions up to 2^24 cells); XNTT_TWIST_TABLE_MAX_MB overrides;
+  // sharded plans and XNTT_COMPACT_TABLES keep the compact two-table form.
+  size_t full_budget = (size_t)512 << 20;
   if (const char* e = std::getenv("XNTT_TWIST_TABLE_MAX_MB")) full_budget = (size_t)std::strtoull(e, nullptr, 10) << 20;
   if ((d->flags & XNTT_COMPACT_TABLES) || shard_count > 1) full_budget = 0;
   {
@@ -463,18 +478,18 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
         words += nlo;
         off_ihi[i] = words;
         words += nhi;
-        const size_t cells = (size_t)1 << lm, dirs_n = (pl->fwd ? 1 : 0) + (pl->inv ? 1 : 0);
-        if (lm <= 31 && cells * dirs_n * sizeof(Tw) <= full_budget) {
-          full_budget -= cells * dirs_n * sizeof(Tw);
-          use_full[i] = 1;
-          if (pl->fwd) {
-            off_ffull[i] = words;
-            words += cells;
-          }
-          if (pl->inv) {
-            off_ifull[i] = words;
-            words += cells;
-          }
+        const size_t cells = (size_t)1 << lm, bytes = cells * sizeof(Tw);
+        if (lm <= 31 && pl->inv && bytes <= full_budget) {
+          full_budget -= bytes;
+          use_ifull[i] = 1;
+          off_ifull[i] = words;
+          words += cells;
+        }
+        if (lm <= 31 && pl->fwd && bytes <= full_budget && (i + 2 == q || bytes <= ((size_t)64 << 20))) {
+          full_budget -= bytes;
+          use_ffull[i] = 1;
+          off_ffull[i] = words;
+          words += cells;
         }
       }
     }
@@ -513,17 +528,15 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
       // the outermost column pass runs last in the inverse: fold 1/inverse_factor into its table
       if (rc == XNTT_OK)
         rc = gen_table(pl->field, base + off_ihi[i], nhi, kPowers, 0, ps.twist_shift, root_big_inv, i == 0 ? finv : 1);
-      if (use_full[i]) {
-        const u32 cells = 1u << lm;
-        if (pl->fwd && rc == XNTT_OK) {
-          ps.fwd_full = base + off_ffull[i];
-          rc = gen_table(pl->field, base + off_ffull[i], cells, kTwist, ps.logn, ps.log_inner, root_big, 1);
-        }
-        if (pl->inv && rc == XNTT_OK) {
-          ps.inv_full = base + off_ifull[i];
-          rc = gen_table(pl->field, base + off_ifull[i], cells, kTwist, ps.logn, ps.log_inner, root_big_inv,
-                         i == 0 ? finv : 1);
-        }
+      const u32 cells = 1u << lm;
+      if (use_ffull[i] && rc == XNTT_OK) {
+        ps.fwd_full = base + off_ffull[i];
+        rc = gen_table(pl->field, base + off_ffull[i], cells, kTwist, ps.logn, ps.log_inner, root_big, 1);
+      }
+      if (use_ifull[i] && rc == XNTT_OK) {
+        ps.inv_full = base + off_ifull[i];
+        rc = gen_table(pl->field, base + off_ifull[i], cells, kTwist, ps.logn, ps.log_inner, root_big_inv,
+                       i == 0 ? finv : 1);
       }
     }
   }

@@ -74,19 +74,18 @@ static int emu_launch2(const PassParams& prm, unsigned grid) {
     tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
     // poison shared memory so that a missing write shows up
     memset(sm.data(), 0xcd, sm.size() * sizeof(sm[0]));
-    // same choice of the twist form as dispatch.cuh: launch_one
-    if (!COL && !INV && !MAP && prm.pointwise != nullptr)
-      emu_stages<F, Cfg, INV, kPointwise>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
-                                          std::make_integer_sequence<int, Cfg::NS>{});
-    else if (!COL)
-      emu_stages<F, Cfg, INV, kNoTwist>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
-                                        std::make_integer_sequence<int, Cfg::NS>{});
-    else if (prm.twist_full != nullptr && !MAP)
-      emu_stages<F, Cfg, INV, kFullTwist>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
-                                          std::make_integer_sequence<int, Cfg::NS>{});
-    else
-      emu_stages<F, Cfg, INV, kCompactTwist>(prm, sm.data(), prm.src + sbase, prm.dst + dbase, col0, row0,
-                                             std::make_integer_sequence<int, Cfg::NS>{});
+    // same choice of the fused extras as dispatch.cuh: launch_one
+    const auto seq = std::make_integer_sequence<int, Cfg::NS>{};
+    const u64 *gs = prm.src + sbase;
+    u64* gd = prm.dst + dbase;
+    switch (pass_kind(COL, INV, MAP, prm)) {
+      case kCompactTwist: emu_stages<F, Cfg, INV, kCompactTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
+      case kFullTwist: emu_stages<F, Cfg, INV, kFullTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
+      case kPointwise: emu_stages<F, Cfg, INV, kPointwise>(prm, sm.data(), gs, gd, col0, row0, seq); break;
+      case kPreTwist: emu_stages<F, Cfg, INV, kPreTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
+      case kPrePointwise: emu_stages<F, Cfg, INV, kPrePointwise>(prm, sm.data(), gs, gd, col0, row0, seq); break;
+      default: emu_stages<F, Cfg, INV, kNoTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
+    }
   }
   return 0;
 }
