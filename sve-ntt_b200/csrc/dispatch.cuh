@@ -46,18 +46,20 @@ cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st)
   return cudaGetLastError();
 }
 
-// one instantiation per kind a pass can take (pass_kernel.cuh: pass_kind); the generalised-addressing kernels of
-// sharded plans only exist in the compact / plain forms (the planner never gives them a matrix)
+// one instantiation per kind a pass can take (pass_kernel.cuh: pass_kind).  The generalised-addressing kernels of
+// sharded plans serve the pass next to the exchange: a column pass there has the compact form, plus what the planner
+// uses for an inner column pass - the whole matrix in the inverse, none at all in the forward direction (the row pass
+// applies it) - and a row pass is always plain.
 template <class F, int LOGN, bool COL, bool INV, bool MAP = false>
 cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
   const int kind = pass_kind(COL, INV, MAP, prm);
   if constexpr (COL) {
     if (kind == kCompactTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist>(prm, grid, st);
-    if constexpr (!MAP) {
+    if constexpr (INV || !MAP) {
       if (kind == kFullTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kFullTwist>(prm, grid, st);
-      if constexpr (!INV) {
-        if (kind == kNoTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
-      }
+    }
+    if constexpr (!INV) {
+      if (kind == kNoTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
     }
     return cudaErrorInvalidValue;
   } else {

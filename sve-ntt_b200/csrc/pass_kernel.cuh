@@ -50,7 +50,7 @@ enum TwistKind { kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2, kPointwise = 3
 // the one place that decides (CUDA dispatcher and host emulator both call it)
 inline int pass_kind(bool col, bool inverse, bool map, const PassParams& prm) {
   if (col) {
-    if (!map && prm.twist_full != nullptr) return kFullTwist;
+    if (prm.twist_full != nullptr) return kFullTwist;
     if (prm.twist_lo != nullptr) return kCompactTwist;
     return kNoTwist;
   }

@@ -132,9 +132,10 @@ int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int
 
 // Forward only: the twiddle matrix of column pass i is applied by the row pass behind it, while that pass loads
 // its rows (contiguous, next to the data, at the start of a tile) instead of at the end of the column pass's tiles.
-// Holds for the last column pass of an unsharded plan whenever the planner stored its forward matrix.
+// Holds for the last column pass whenever the planner stored its forward matrix (never for the column-sharded
+// first pass of a sharded plan).
 bool row_applies_twist(const xntt_plan* pl, size_t i) {
-  return pl->shard_count == 1 && i + 2 == pl->passes.size() && pl->passes[i].fwd_full != nullptr;
+  return i + 2 == pl->passes.size() && pl->passes[i].fwd_full != nullptr;
 }
 
 // One pass.  `count_override` (when non-zero) replaces the number of outer blocks / rows: the row
@@ -301,8 +302,9 @@ int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const
     prm.twist_lo = inverse ? ps.inv_lo : ps.fwd_lo;
     prm.twist_hi = inverse ? ps.inv_hi : ps.fwd_hi;
     prm.twist_shift = (u32)ps.twist_shift;
-    prm.twist_full = inverse ? ps.inv_full : ps.fwd_full;
+    prm.twist_full = inverse ? ps.inv_full : nullptr;  // forward: compact, or none when the row pass applies it
     prm.twist_full_shift = (u32)ps.log_inner;
+    if (!inverse && row_applies_twist(pl, i)) prm.twist_lo = prm.twist_hi = nullptr;
     prm.twist_col0 = twist_col0;
     const u64 tiles = units * tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -447,10 +449,10 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   // column pass of a three-pass plan is read at the end of that pass's tiles, which pays off while the matrix
   // stays L2-resident (<= 64 MiB).  2^24: column pass 228 -> 180 us forward, 241 -> 228 us inverse.
   // Default budget 512 MiB per plan (both directions up to 2^24 cells); XNTT_TWIST_TABLE_MAX_MB overrides;
-  // sharded plans and XNTT_COMPACT_TABLES keep the compact two-table form.
+  // XNTT_COMPACT_TABLES and the column-sharded first pass of a sharded plan keep the compact two-table form.
   size_t full_budget = (size_t)512 << 20;
   if (const char* e = std::getenv("XNTT_TWIST_TABLE_MAX_MB")) full_budget = (size_t)std::strtoull(e, nullptr, 10) << 20;
-  if ((d->flags & XNTT_COMPACT_TABLES) || shard_count > 1) full_budget = 0;
+  if (d->flags & XNTT_COMPACT_TABLES) full_budget = 0;
   {
     int rem = pl->log2_m, before = 0;
     for (size_t i = 0; i < q; ++i) {
@@ -479,13 +481,15 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
         off_ihi[i] = words;
         words += nhi;
         const size_t cells = (size_t)1 << lm, bytes = cells * sizeof(Tw);
-        if (lm <= 31 && pl->inv && bytes <= full_budget) {
+        const bool eligible = lm <= 31 && !(shard_count > 1 && i == 0);  // a sharded first pass only sees its columns
+        if (eligible && pl->inv && bytes <= full_budget) {
           full_budget -= bytes;
           use_ifull[i] = 1;
           off_ifull[i] = words;
           words += cells;
         }
-        if (lm <= 31 && pl->fwd && bytes <= full_budget && (i + 2 == q || bytes <= ((size_t)64 << 20))) {
+        // forward: the last column pass (any plan), or an outer pass of an unsharded plan while it stays in L2
+        if (eligible && pl->fwd && bytes <= full_budget && (i + 2 == q || (shard_count == 1 && bytes <= ((size_t)64 << 20)))) {
           full_budget -= bytes;
           use_ffull[i] = 1;
           off_ffull[i] = words;
