@@ -63,9 +63,9 @@ def measured_peaks():
 
 def ncu_traffic(workload, splits, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
-    ncu --set full capture of this very command (profiles/r1_v3_ncu_pass_kernels.json); None when the
+    ncu --set full capture of this very command (profiles/r1_v4_ncu_pass_kernels.json); None when the
     capture does not cover the configuration."""
-    path = os.path.join(ROOT, "profiles", "r1_v3_ncu_pass_kernels.json")
+    path = os.path.join(ROOT, "profiles", "r1_v4_ncu_pass_kernels.json")
     if workload != "ntt24" or list(splits) != [11, 13] or not os.path.exists(path):
         return None
     order = ["fwd_pass0_2^11", "fwd_pass1_2^13", "inv_pass1_2^13", "inv_pass0_2^11"]  # launch order in the capture
@@ -305,7 +305,10 @@ def main():
                     "peak_source": peak_src,
                     "alg_bytes_per_launch": 16 * local_words,
                     "note": "kernel reads and writes every residue once: 16 B/element per launch; the kernels are "
-                            "bound by the IMAD pipe, see roofline_int"}
+                            "bound by the IMAD pipe, see roofline_int.  traffic (ncu dram bytes of this launch) also "
+                            "holds the 16 B/element twiddle matrix the row pass / inverse column pass streams where the "
+                            "plan stores one (DESIGN.md section 2): spare HBM bandwidth traded for one modular product "
+                            "per residue, not a re-read of data"}
 
     # ---- integer roofline: measured IMAD / IMAD.WIDE rates ------------------------------------------
     roofline_int = None
