@@ -286,7 +286,10 @@ int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, 
 int launch_transpose(u64* dst, const u64* src, u64 rows, u64 cols, u64 ld_dst, u64 ld_src, void* stream) {
   TransposeParams p{dst, src, rows, cols, ld_dst, ld_src, (u32)((cols + kTrTile - 1) / kTrTile)};
   const u64 tiles_r = (rows + kTrTile - 1) / kTrTile;
-  static bool attr_done = false;
+  static bool attr_done_on[64] = {};  // per device, like the pass kernels (dispatch.cuh)
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  bool& attr_done = attr_done_on[dev & 63];
   if (!attr_done) {
     CU(cudaFuncSetAttribute(transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(kTrSmemWords * sizeof(u64))));

@@ -26,9 +26,14 @@ cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st)
   constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
   auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, TWIST, MAP>;
-  static bool attr_done = false;
+  // function attributes live in the context of the device they were set on: once per kernel and device
+  static bool attr_done_on[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  bool& attr_done = attr_done_on[dev & 63];
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
 #ifndef XNTT_CARVE_TILES
 #define XNTT_CARVE_TILES XNTT_MINB

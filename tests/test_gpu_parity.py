@@ -494,3 +494,28 @@ def test_sharded_transform_on_two_gpus():
         rank, res = q.get(timeout=5)
         for want_mode, got_mode, ok_f, ok_i in res:
             assert ok_f and ok_i, (rank, want_mode, got_mode)
+
+
+def test_two_devices_in_one_process(cuda_lib, oracle):
+    """xntt_desc::device: plans on different GPUs of one process (kernel attributes are per device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L = 16
+    a = oracle.fill_xorshift(1 << L, SEED + 77, P0)
+    want = oracle.ntt_forward(a, P0, G0)
+    for dev_id in (1, 0):
+        plan = cuda_lib.plan(L, device=dev_id)
+        with torch.cuda.device(dev_id):
+            d = torch.from_numpy(a.view(np.int64)).cuda(dev_id)
+            o = torch.empty_like(d)
+            plan.forward(o.data_ptr(), d.data_ptr(), torch.cuda.current_stream(dev_id).cuda_stream)
+            torch.cuda.synchronize(dev_id)
+            assert np.array_equal(o.cpu().numpy().view(np.uint64), want), dev_id
+            t = torch.empty((256, 128), dtype=torch.int64, device=f"cuda:{dev_id}")
+            src = torch.arange(128 * 256, dtype=torch.int64, device=f"cuda:{dev_id}").view(128, 256)
+            cuda_lib.transpose(t.data_ptr(), src.data_ptr(), 128, 256, 128, 256,
+                               torch.cuda.current_stream(dev_id).cuda_stream)
+            torch.cuda.synchronize(dev_id)
+            assert torch.equal(t, src.t())
+        plan.close()
