@@ -443,6 +443,23 @@ __device__ __forceinline__ void inv_network(const F& f, u64 (&x)[1 << LOGR][C], 
 // (LOGS = the smaller of the two strides), and in both stages the tasks of one block sit on the same GT
 // consecutive threads (GT = 2^LOGS, times the column groups in column mode) in the same loop iteration - so only
 // those threads have to meet: a warp-level barrier for the innermost exchange, a named barrier for the next one.
+#ifndef XNTT_GROUP_BARRIERS
+#define XNTT_GROUP_BARRIERS 1
+#endif
+// number of consecutive threads that have to meet after stage J (kThreads = the whole CTA)
+template <class Cfg, bool INVERSE, int J>
+constexpr int barrier_group() {
+  constexpr int NS = Cfg::NS;
+  constexpr int NTASK8 = (1 << (Cfg::LOGN - 3)) * Cfg::NP;  // tasks of a radix-8 stage
+  // stride of the finer of the two stages around the exchange
+  constexpr int LOGS = INVERSE ? 3 * (J + 1) : 3 * (NS - 1 - J);
+  // both stages radix 8: the first forward / last inverse stage has radix 2^LOGR1
+  constexpr bool both8 = (INVERSE ? (J + 1 < NS - 1 || Cfg::LOGR1 == 3) : (J >= 1 || Cfg::LOGR1 == 3)) && NTASK8 >= kThreads;
+  if (!XNTT_GROUP_BARRIERS || !both8 || LOGS > 8) return kThreads;
+  const int gt = (1 << LOGS) * (Cfg::COL ? Cfg::NP : 1);
+  return gt < kThreads ? gt : kThreads;
+}
+
 template <int GT>
 __device__ __forceinline__ void stage_barrier() {
 #if !defined(XNTT_HOST_EMU)
@@ -459,9 +476,6 @@ __device__ __forceinline__ void stage_barrier() {
 #define XNTT_TASK_UNROLL 1
 #endif
 constexpr int kTaskUnroll = XNTT_TASK_UNROLL;  // tasks of one stage a thread works on at a time
-#ifndef XNTT_GROUP_BARRIERS
-#define XNTT_GROUP_BARRIERS 1
-#endif
 
 // ---------------------------------------------------------------------------------------------
 template <class F, class Cfg, int TWIST, int J>
@@ -528,11 +542,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
       smem_store<Cfg, R>(sm, k0, LOGS, p, x);
     }
   }
-  if constexpr (J != NS - 1) {
-    constexpr bool kBothRadix8 = (J >= 1 || Cfg::LOGR1 == 3) && NTASK >= kThreads;
-    constexpr int GT = (XNTT_GROUP_BARRIERS && kBothRadix8 && LOGS <= 8) ? (1 << LOGS) * (Cfg::COL ? Cfg::NP : 1) : kThreads;
-    stage_barrier<(GT < kThreads ? GT : kThreads)>();
-  }
+  if constexpr (J != NS - 1) stage_barrier<barrier_group<Cfg, false, J>()>();
 }
 
 template <class F, class Cfg, int TWIST, int J>
@@ -584,12 +594,7 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
       smem_store<Cfg, R>(sm, k0, LOGS, p, x);
     }
   }
-  if constexpr (J != NS - 1) {
-    // the next stage (stride 2^(LOGS + 3)) is radix 8 unless it is the last one of a length that is not 8^k
-    constexpr bool kBothRadix8 = (J + 1 < NS - 1 || Cfg::LOGR1 == 3) && NTASK >= kThreads;
-    constexpr int GT = (XNTT_GROUP_BARRIERS && kBothRadix8 && LOGS + 3 <= 8) ? (1 << (LOGS + 3)) * (Cfg::COL ? Cfg::NP : 1) : kThreads;
-    stage_barrier<(GT < kThreads ? GT : kThreads)>();
-  }
+  if constexpr (J != NS - 1) stage_barrier<barrier_group<Cfg, true, J>()>();
 }
 
 template <class F, class Cfg, bool INVERSE, int TWIST, int... Js>

@@ -43,10 +43,15 @@ static inline unsigned __brev(unsigned v) {
 
 namespace xntt {
 
+// Emulated schedule.  A stage ends with a barrier over barrier_group<>() consecutive threads (pass_kernel.cuh:
+// stage_barrier), not necessarily the whole CTA.  The emulator runs the most eager schedule those barriers allow:
+// a group of threads goes as deep into the stages as its barriers permit before the next group has run anything -
+// so a barrier group that is too small (a stage reading a slot another group has not written yet, or overwriting one
+// another group still has to read) produces wrong words, the tile having been poisoned beforehand.
 template <class F, class Cfg, bool INV, int TWIST, int J>
-static void emu_stage_all_threads(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc,
-                                  u64* gdst, u32 col0, u32 row0) {
-  for (unsigned t = 0; t < (unsigned)kThreads; ++t) {
+static void emu_stage_threads(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc, u64* gdst,
+                              u32 col0, u32 row0, unsigned t0, unsigned t1) {
+  for (unsigned t = t0; t < t1; ++t) {
     threadIdx.x = t;
     if constexpr (INV)
       inv_stage<F, Cfg, TWIST, J>(prm, sm, gsrc, gdst, col0, row0);
@@ -55,11 +60,44 @@ static void emu_stage_all_threads(const PassParams& prm, typename Slot<Cfg::C>::
   }
 }
 
+// forward: groups shrink from stage to stage.  [t0, t1) may start stage J; each barrier group of the barrier
+// after stage J runs stage J and then goes on alone
+template <class F, class Cfg, int TWIST, int J>
+static void emu_fwd_from(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc, u64* gdst, u32 col0,
+                         u32 row0, unsigned t0, unsigned t1) {
+  unsigned step = 1;  // after the last stage nobody waits for anybody
+  if constexpr (J + 1 < Cfg::NS) step = barrier_group<Cfg, false, J>();
+  if (step > t1 - t0) step = t1 - t0;
+  for (unsigned g = t0; g < t1; g += step) {
+    emu_stage_threads<F, Cfg, false, TWIST, J>(prm, sm, gsrc, gdst, col0, row0, g, g + step);
+    if constexpr (J + 1 < Cfg::NS) emu_fwd_from<F, Cfg, TWIST, J + 1>(prm, sm, gsrc, gdst, col0, row0, g, g + step);
+  }
+}
+// inverse: groups grow.  [t0, t1) is one barrier group of the barrier after stage J - 1 (a single thread for
+// J = 0): bring each of its sub-groups through stage J - 1, then run stage J on it
+template <class F, class Cfg, int TWIST, int J>
+static void emu_inv_upto(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc, u64* gdst, u32 col0,
+                         u32 row0, unsigned t0, unsigned t1) {
+  if constexpr (J > 0) {
+    unsigned step = 1;
+    if constexpr (J > 1) step = barrier_group<Cfg, true, J - 2>();
+    if (step > t1 - t0) step = t1 - t0;
+    for (unsigned g = t0; g < t1; g += step) emu_inv_upto<F, Cfg, TWIST, J - 1>(prm, sm, gsrc, gdst, col0, row0, g, g + step);
+  }
+  emu_stage_threads<F, Cfg, true, TWIST, J>(prm, sm, gsrc, gdst, col0, row0, t0, t1);
+}
+
 template <class F, class Cfg, bool INV, int TWIST, int... Js>
 static void emu_stages(const PassParams& prm, typename Slot<Cfg::C>::type* sm, const u64* gsrc, u64* gdst,
                        u32 col0, u32 row0, std::integer_sequence<int, Js...>) {
-  // a stage ends with a block-wide barrier: run every emulated thread through stage J, then J + 1
-  (emu_stage_all_threads<F, Cfg, INV, TWIST, Js>(prm, sm, gsrc, gdst, col0, row0), ...);
+  if constexpr (INV) {
+    unsigned step = 1;
+    if constexpr (Cfg::NS > 1) step = barrier_group<Cfg, true, Cfg::NS - 2>();
+    for (unsigned g = 0; g < (unsigned)kThreads; g += step)
+      emu_inv_upto<F, Cfg, TWIST, Cfg::NS - 1>(prm, sm, gsrc, gdst, col0, row0, g, g + step);
+  } else {
+    emu_fwd_from<F, Cfg, TWIST, 0>(prm, sm, gsrc, gdst, col0, row0, 0, (unsigned)kThreads);
+  }
 }
 
 template <class F, int LOGN, bool COL, bool INV, bool MAP>
