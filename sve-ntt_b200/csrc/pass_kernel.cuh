@@ -448,7 +448,7 @@ __device__ __forceinline__ void inv_network(const F& f, u64 (&x)[1 << LOGR][C], 
 #endif
 // number of consecutive threads that have to meet after stage J (kThreads = the whole CTA)
 template <class Cfg, bool INVERSE, int J>
-constexpr int barrier_group() {
+__host__ __device__ constexpr int barrier_group() {
   constexpr int NS = Cfg::NS;
   constexpr int NTASK8 = (1 << (Cfg::LOGN - 3)) * Cfg::NP;  // tasks of a radix-8 stage
   // stride of the finer of the two stages around the exchange
