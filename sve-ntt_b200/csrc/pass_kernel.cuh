@@ -61,11 +61,22 @@ inline int pass_kind(bool col, bool inverse, bool map, const PassParams& prm) {
   return kNoTwist;
 }
 
-template <int LOGN>
+// Stage radices of a pass of length 2^LOGN: the first forward (= last inverse) stage has radix 2^LOGR1, every other
+// stage radix 2^LOGRN.  LOGRN = 3 (radix 8) everywhere, except - with XNTT_RADIX16 - tiles with one residue per slot
+// (C = 1, in the default build the 2^13 rows), which run radix 16 with a first stage of up to radix 32: 13 = 5 + 4 + 4,
+// one shared-memory exchange less than 4 + 3 + 3 + 3.  Measured on B200: no gain (2^13 rows 229.5 vs 230.1 us forward,
+// 204.5 vs 205.2 us inverse at 128 instead of 88-108 registers; with every tile at C = 1 the 2^12 rows gain 3 % forward
+// and lose 5 % inverse) - the exchanges are not what the passes wait for - so it stays off.
+#ifndef XNTT_RADIX16
+#define XNTT_RADIX16 0
+#endif
+template <int LOGN, int C>
 struct Stages {
+  static constexpr int LOGRN = (XNTT_RADIX16 && C == 1) ? 4 : 3;
   static constexpr int kRem = LOGN % 3;
-  static constexpr int LOGR1 = LOGN <= 4 ? LOGN : (kRem == 0 ? 3 : (kRem == 1 ? 4 : 2));
-  static constexpr int NS = 1 + (LOGN - LOGR1) / 3;
+  static constexpr int LOGR1 = LOGRN == 3 ? (LOGN <= 4 ? LOGN : (kRem == 0 ? 3 : (kRem == 1 ? 4 : 2)))
+                                          : (LOGN <= 5 ? LOGN : LOGN - 4 * ((LOGN - 5 + 3) / 4));
+  static constexpr int NS = 1 + (LOGN - LOGR1) / LOGRN;
 };
 
 template <int C>
@@ -81,9 +92,9 @@ struct Slot<2> {
   static constexpr int kSwzMask = 7;
 };
 
-template <int C>
+template <int C, int LOGRN>
 __device__ __forceinline__ int swz(int k) {
-  return k ^ ((k >> 3) & Slot<C>::kSwzMask);
+  return k ^ ((k >> LOGRN) & Slot<C>::kSwzMask);
 }
 
 template <int LOGN_, int LOGW_, int C_, bool COL_, bool MAP_ = false>
@@ -93,8 +104,9 @@ struct PassCfg {
   static constexpr int N = 1 << LOGN, W = 1 << LOGW;
   static constexpr int NP = W / C;  // column groups per tile
   static constexpr int LOGNP = LOGW - (C == 2 ? 1 : 0);
-  static constexpr int LOGR1 = Stages<LOGN>::LOGR1;
-  static constexpr int NS = Stages<LOGN>::NS;
+  static constexpr int LOGRN = Stages<LOGN, C>::LOGRN;
+  static constexpr int LOGR1 = Stages<LOGN, C>::LOGR1;
+  static constexpr int NS = Stages<LOGN, C>::NS;
   static constexpr size_t kSmemBytes = NS > 1 ? (size_t)N * W * sizeof(u64) : 0;
   static_assert(W >= C, "tile narrower than a column group");
 };
@@ -102,9 +114,9 @@ struct PassCfg {
 template <class Cfg>
 __device__ __forceinline__ int slot_index(int k, int p) {
   if constexpr (Cfg::COL)
-    return (swz<Cfg::C>(k) << Cfg::LOGNP) + p;
+    return (swz<Cfg::C, Cfg::LOGRN>(k) << Cfg::LOGNP) + p;
   else
-    return (p << Cfg::LOGN) + swz<Cfg::C>(k);
+    return (p << Cfg::LOGN) + swz<Cfg::C, Cfg::LOGRN>(k);
 }
 
 template <class Cfg, int R>
@@ -269,15 +281,6 @@ __device__ __forceinline__ Tw ld_tw(const Tw* t) {
   return r;
 }
 
-// Hint the twiddles a later stage will use into L1 (no register cost): the last stages read one table entry per
-// butterfly, and with 4 warps per scheduler an L1 miss there is exposed latency.
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-#if !defined(XNTT_HOST_EMU)
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
 #if !defined(XNTT_HOST_EMU)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -285,37 +288,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   (void)p;
 #endif
 }
-#ifndef XNTT_PREFETCH_TW
-#define XNTT_PREFETCH_TW 0
-#endif
-
-// forward stage J's twiddles of this thread's tasks: G[(B << lam) + g], lam < LOGR, g < 2^lam
-template <class Cfg, int J>
-__device__ __forceinline__ void prefetch_fwd_stage(const Tw* __restrict__ G) {
-  constexpr int NS = Cfg::NS;
-  constexpr int LOGR = (J == 0) ? Cfg::LOGR1 : 3;
-  constexpr int LOGS = 3 * (NS - 1 - J);
-  constexpr int LOGT = Cfg::LOGN - LOGR;
-  constexpr int NTASK = (1 << LOGT) * Cfg::NP;
-  if constexpr (LOGS <= 3) {  // earlier stages share each entry between >= 64 tasks: nothing to hide
-#pragma unroll 1
-    for (int task = threadIdx.x; task < NTASK; task += kThreads) {
-      int t;
-      if constexpr (Cfg::COL)
-        t = task >> Cfg::LOGNP;
-      else
-        t = task & ((1 << LOGT) - 1);
-      const int B = t >> LOGS;
-#pragma unroll
-      for (int lam = 0; lam < LOGR; ++lam) {
-        // 2^lam consecutive 16-byte entries: one 128-byte line holds 8
-#pragma unroll
-        for (int g = 0; g < (1 << lam); g += 8) prefetch_l1(G + ((B << lam) + g));
-      }
-    }
-  }
-}
-
 // Six-step twiddle of element (k, global column col): omega_M^(bitrev_LOGN(k) * col).  Two forms:
 //   * prm.twist_full set: the plan holds the whole twiddle matrix in the layout of the data (entry (k, col)
 //     next to entry (k, col + 1)); the twist is one streamed load and ONE Montgomery product.  The load is as
@@ -365,17 +337,19 @@ __device__ __forceinline__ void apply_twist(const F& f, const PassParams& prm, u
 template <class F, class Cfg, int R>
 __device__ __forceinline__ void apply_pre_twist(const F& f, const PassParams& prm, u64 (&x)[R][Cfg::C], int k0, int logs,
                                                 u32 row) {
-  Tw t[R][Cfg::C];
+  constexpr int CH = R < 16 ? R : 16;  // entries in flight at a time (4 registers each)
 #pragma unroll
   for (int c = 0; c < Cfg::C; ++c) {
     const Tw* q = prm.pre_twist + ((u64)((row + c) & prm.pre_rows_mask) << Cfg::LOGN);  // the mask keeps ragged tiles in range
 #pragma unroll
-    for (int r = 0; r < R; ++r) t[r][c] = ld_tw_stream(q + (k0 + (r << logs)));
+    for (int r0 = 0; r0 < R; r0 += CH) {
+      Tw t[CH];
+#pragma unroll
+      for (int r = 0; r < CH; ++r) t[r] = ld_tw_stream(q + (k0 + ((r0 + r) << logs)));
+#pragma unroll
+      for (int r = 0; r < CH; ++r) x[r0 + r][c] = f.mont(x[r0 + r][c], t[r]);
+    }
   }
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], t[r][c]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,7 +413,7 @@ __device__ __forceinline__ void inv_network(const F& f, u64 (&x)[1 << LOGR][C], 
   }
 }
 
-// Barrier between two adjacent radix-8 stages.  Their exchange is closed over blocks of 8 * 2^LOGS consecutive k
+// Barrier between two adjacent stages of the same radix R.  Their exchange is closed over blocks of R * 2^LOGS consecutive k
 // (LOGS = the smaller of the two strides), and in both stages the tasks of one block sit on the same GT
 // consecutive threads (GT = 2^LOGS, times the column groups in column mode) in the same loop iteration - so only
 // those threads have to meet: a warp-level barrier for the innermost exchange, a named barrier for the next one.
@@ -449,13 +423,13 @@ __device__ __forceinline__ void inv_network(const F& f, u64 (&x)[1 << LOGR][C], 
 // number of consecutive threads that have to meet after stage J (kThreads = the whole CTA)
 template <class Cfg, bool INVERSE, int J>
 __host__ __device__ constexpr int barrier_group() {
-  constexpr int NS = Cfg::NS;
-  constexpr int NTASK8 = (1 << (Cfg::LOGN - 3)) * Cfg::NP;  // tasks of a radix-8 stage
+  constexpr int NS = Cfg::NS, LR = Cfg::LOGRN;
+  constexpr int NTASKR = (1 << (Cfg::LOGN - LR)) * Cfg::NP;  // tasks of a stage of the common radix
   // stride of the finer of the two stages around the exchange
-  constexpr int LOGS = INVERSE ? 3 * (J + 1) : 3 * (NS - 1 - J);
-  // both stages radix 8: the first forward / last inverse stage has radix 2^LOGR1
-  constexpr bool both8 = (INVERSE ? (J + 1 < NS - 1 || Cfg::LOGR1 == 3) : (J >= 1 || Cfg::LOGR1 == 3)) && NTASK8 >= kThreads;
-  if (!XNTT_GROUP_BARRIERS || !both8 || LOGS > 8) return kThreads;
+  constexpr int LOGS = INVERSE ? LR * (J + 1) : LR * (NS - 1 - J);
+  // both stages of the common radix: the first forward / last inverse stage has radix 2^LOGR1
+  constexpr bool same = (INVERSE ? (J + 1 < NS - 1 || Cfg::LOGR1 == LR) : (J >= 1 || Cfg::LOGR1 == LR)) && NTASKR >= kThreads;
+  if (!XNTT_GROUP_BARRIERS || !same || LOGS > 8) return kThreads;
   const int gt = (1 << LOGS) * (Cfg::COL ? Cfg::NP : 1);
   return gt < kThreads ? gt : kThreads;
 }
@@ -483,14 +457,11 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
                                           const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
   const F f = make_field<F>(prm.field);
   constexpr int NS = Cfg::NS;
-  constexpr int LOGR = (J == 0) ? Cfg::LOGR1 : 3;
+  constexpr int LOGR = (J == 0) ? Cfg::LOGR1 : Cfg::LOGRN;
   constexpr int R = 1 << LOGR;
-  constexpr int LOGS = 3 * (NS - 1 - J);
+  constexpr int LOGS = Cfg::LOGRN * (NS - 1 - J);
   constexpr int LOGT = Cfg::LOGN - LOGR;  // tasks per sub-transform
   constexpr int NTASK = (1 << LOGT) * Cfg::NP;
-#if XNTT_PREFETCH_TW
-  if constexpr (J + 1 < NS) prefetch_fwd_stage<Cfg, J + 1>(prm.tw);
-#endif
 #pragma unroll(kTaskUnroll)
   for (int task = threadIdx.x; task < NTASK; task += kThreads) {
     int p, t;
@@ -551,9 +522,9 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
   const F f = make_field<F>(prm.field);
   constexpr int NS = Cfg::NS;
   // inverse stage J mirrors forward stage NS-1-J
-  constexpr int LOGR = (J == NS - 1) ? Cfg::LOGR1 : 3;
+  constexpr int LOGR = (J == NS - 1) ? Cfg::LOGR1 : Cfg::LOGRN;
   constexpr int R = 1 << LOGR;
-  constexpr int LOGS = 3 * J;
+  constexpr int LOGS = Cfg::LOGRN * J;
   constexpr int LOGT = Cfg::LOGN - LOGR;
   constexpr int NTASK = (1 << LOGT) * Cfg::NP;
 #pragma unroll(kTaskUnroll)
