@@ -156,10 +156,10 @@ struct FieldOps : K {
   // Montgomery product pieces: returns h1 = hi64(a*w), h2 = hi64(q*P) with q = a*w' mod 2^64;
   // a*omega == h1 - h2 (mod P), the true difference lying in (-P, P).  `a` may be lazy.
   //
-  // On sm_100a IMAD.WIDE issues at half the IMAD rate (measured: 8.0 vs 18.5 Tinstr/s), so the
-  // 32x32->64 products are what the kernel is bound by.  Only six of them (+ one IMAD.HI) are
-  // needed instead of the eight a pair of mul.hi.u64 would issue: the low 64 bits of a*w and q*P
-  // are equal by construction, so the carry out of the low half of q*P follows from the low half
+  // On sm_100a IMAD.WIDE issues at well under half the IMAD rate (measured: 8.0 vs 18.5 Tinstr/s), so the
+  // 32x32->64 products are what the kernel is bound by.  Seven of them are needed here (four for a*w, three for
+  // q*P; the eighth is the low product a*w') instead of the eight of a pair of mul.hi.u64: the low 64 bits of
+  // a*w and q*P are equal by construction, so the carry out of the low half of q*P follows from the low half
   // of a*w:  carry2 = [L.hi < lo32(q0*P1 + q1*P0)]  with  L.hi = bits 32..63 of a*w.
   __device__ __forceinline__ void mont_parts(u64 a, u64 w, u64 wp, u64& h1, u64& h2) const {
     const u64 P = this->p();

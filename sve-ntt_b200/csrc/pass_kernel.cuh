@@ -2,7 +2,8 @@
 //
 // One "pass" of the (blocked) six-step NTT: every CTA owns a tile of W independent length-N
 // sub-transforms, keeps it resident in shared memory, and runs all log2(N) butterfly levels on it
-// as radix-8 (first stage radix 4/8/16) register passes with swizzled shared-memory exchanges.
+// as radix-8 (first stage radix 4/8/16) register passes with swizzled shared-memory exchanges and
+// barriers that only span the threads an exchange connects.
 //
 //   column mode : data is [outer][N][inner]; the tile is N rows x W contiguous columns
 //                 (element (k, c) at base + k*inner + c).  This is the column phase of
@@ -10,7 +11,7 @@
 //                 (include/sventt/layer/sve/blocked-generic.hpp:121-155): its tile transpose-in /
 //                 inner NTT / transpose-out becomes "strided tile load -> NTT -> strided store",
 //                 and the row twiddle of sventt::GenericSVELayer::twiddle_rows_forward
-//                 (include/sventt/layer/sve/generic.hpp:169-268) is fused into the last stage.
+//                 (include/sventt/layer/sve/generic.hpp:169-268) is fused into a pass boundary (TwistKind).
 //   row mode    : data is [rows][N]; the tile is W whole rows (element (k, c) at base + c*N + k).
 //                 This is the inner kernel call of sventt::RecursiveNTT::compute_forward
 //                 (include/sventt/kernel/recursive.hpp:69-74).
