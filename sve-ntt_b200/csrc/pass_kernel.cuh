@@ -112,20 +112,34 @@ struct PassCfg {
   static_assert(W >= C, "tile narrower than a column group");
 };
 
-template <class Cfg>
-__device__ __forceinline__ int slot_index(int k, int p) {
-  if constexpr (Cfg::COL)
-    return (swz<Cfg::C, Cfg::LOGRN>(k) << Cfg::LOGNP) + p;
-  else
-    return (p << Cfg::LOGN) + swz<Cfg::C, Cfg::LOGRN>(k);
-}
-
-template <class Cfg, int R>
-__device__ __forceinline__ void smem_load(const typename Slot<Cfg::C>::type* sm, int k0, int logs, int p,
-                                          u64 (&x)[R][Cfg::C]) {
+// Slot of element k0 + (r << logs) of a task.  The swizzle is linear over GF(2) and k0 has no bits where
+// r << logs has any, so swz(k0 + (r << logs)) = swz(k0) ^ swz(r << logs) with the second term a compile-time
+// constant: one swizzle per task, then an XOR with the constant's low bits (often none) plus a constant offset
+// that folds into the address immediate - instead of shift / xor / shift-add per slot.
+template <class Cfg, int LOGS, int R>
+__device__ __forceinline__ void task_slots(int k0, int p, int (&idx)[R]) {
+  constexpr int MB = Slot<Cfg::C>::kSwzMask == 15 ? 4 : 3;  // the swizzle rewrites bits [0, MB)
+  constexpr int LOW = (1 << MB) - 1;
+  const int b = swz<Cfg::C, Cfg::LOGRN>(k0);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    auto v = sm[slot_index<Cfg>(k0 + (r << logs), p)];
+    const int cr = (r << LOGS) ^ (((r << LOGS) >> Cfg::LOGRN) & Slot<Cfg::C>::kSwzMask);
+    // above bit MB the constant only has bits of r << logs, which b does not have: add (-> address immediate)
+    const int s = LOGS >= MB ? ((b ^ (cr & LOW)) + (cr & ~LOW)) : (b ^ cr);
+    if constexpr (Cfg::COL)
+      idx[r] = (s << Cfg::LOGNP) + p;
+    else
+      idx[r] = (p << Cfg::LOGN) + s;
+  }
+}
+
+template <class Cfg, int LOGS, int R>
+__device__ __forceinline__ void smem_load(const typename Slot<Cfg::C>::type* sm, int k0, int p, u64 (&x)[R][Cfg::C]) {
+  int idx[R];
+  task_slots<Cfg, LOGS, R>(k0, p, idx);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    auto v = sm[idx[r]];
     if constexpr (Cfg::C == 2) {
       x[r][0] = v.x;
       x[r][1] = v.y;
@@ -135,15 +149,16 @@ __device__ __forceinline__ void smem_load(const typename Slot<Cfg::C>::type* sm,
   }
 }
 
-template <class Cfg, int R>
-__device__ __forceinline__ void smem_store(typename Slot<Cfg::C>::type* sm, int k0, int logs, int p,
-                                           const u64 (&x)[R][Cfg::C]) {
+template <class Cfg, int LOGS, int R>
+__device__ __forceinline__ void smem_store(typename Slot<Cfg::C>::type* sm, int k0, int p, const u64 (&x)[R][Cfg::C]) {
+  int idx[R];
+  task_slots<Cfg, LOGS, R>(k0, p, idx);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if constexpr (Cfg::C == 2) {
-      sm[slot_index<Cfg>(k0 + (r << logs), p)] = make_ulonglong2(x[r][0], x[r][1]);
+      sm[idx[r]] = make_ulonglong2(x[r][0], x[r][1]);
     } else {
-      sm[slot_index<Cfg>(k0 + (r << logs), p)] = x[r][0];
+      sm[idx[r]] = x[r][0];
     }
   }
 }
@@ -481,7 +496,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
       if constexpr (TWIST == kPreTwist || TWIST == kPrePointwise)
         apply_pre_twist<F, Cfg, R>(f, prm, x, k0, LOGS, row0 + (u32)(p * Cfg::C));
     } else {
-      smem_load<Cfg, R>(sm, k0, LOGS, p, x);
+      smem_load<Cfg, LOGS, R>(sm, k0, p, x);
     }
     fwd_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, B);
     if constexpr (J == NS - 1) {
@@ -511,7 +526,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
       }
       gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
     } else {
-      smem_store<Cfg, R>(sm, k0, LOGS, p, x);
+      smem_store<Cfg, LOGS, R>(sm, k0, p, x);
     }
   }
   if constexpr (J != NS - 1) stage_barrier<barrier_group<Cfg, false, J>()>();
@@ -546,7 +561,7 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
       if constexpr (TWIST == kCompactTwist || TWIST == kFullTwist)
         apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
     } else {
-      smem_load<Cfg, R>(sm, k0, LOGS, p, x);
+      smem_load<Cfg, LOGS, R>(sm, k0, p, x);
     }
     inv_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, LOGS, i);
     if constexpr (J == NS - 1) {
@@ -563,7 +578,7 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
       }
       gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
     } else {
-      smem_store<Cfg, R>(sm, k0, LOGS, p, x);
+      smem_store<Cfg, LOGS, R>(sm, k0, p, x);
     }
   }
   if constexpr (J != NS - 1) stage_barrier<barrier_group<Cfg, true, J>()>();
