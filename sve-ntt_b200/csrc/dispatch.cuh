@@ -63,15 +63,17 @@ cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
     if constexpr (INV || !MAP) {
       if (kind == kFullTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kFullTwist>(prm, grid, st);
     }
-    if constexpr (!INV) {
-      if (kind == kNoTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
-    }
+    // twist-free: the row pass next to it applies the matrix
+    if (kind == kNoTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
     return cudaErrorInvalidValue;
   } else {
     if constexpr (!INV && !MAP) {
       if (kind == kPointwise) return launch_kernel<F, LOGN, COL, INV, MAP, kPointwise>(prm, grid, st);
       if (kind == kPreTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kPreTwist>(prm, grid, st);
       if (kind == kPrePointwise) return launch_kernel<F, LOGN, COL, INV, MAP, kPrePointwise>(prm, grid, st);
+    }
+    if constexpr (INV && !MAP) {
+      if (kind == kPostTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kPostTwist>(prm, grid, st);
     }
     return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
   }

@@ -64,8 +64,9 @@ struct PassParams {
   u64 inner;           // column mode: elements between consecutive k; row mode: unused
   u64 outer_stride;    // column mode: elements between consecutive outer blocks (= N * inner)
   u32 tiles_per_outer; // column mode: inner / W
-  const Tw* pre_twist;   // forward row pass: the twiddle matrix of the column pass before it, applied while the rows are
-                         // loaded (entry ((row & pre_rows_mask) << log2 N) + k); that column pass then runs without
+  const Tw* pre_twist;   // row pass: the twiddle matrix of the column pass next to it (entry ((row & pre_rows_mask) <<
+                         // log2 N) + k), applied while the rows are loaded (forward) or before they are stored
+                         // (inverse); that column pass then runs without a twiddle
   u32 pre_rows_mask;
   u32 twist_shift;
   u32 twist_full_shift;  // log2 of the number of columns of twist_full

@@ -46,7 +46,11 @@ namespace xntt {
 //                   rows of the matrix next to contiguous rows of data, at the start of a tile where the latency
 //                   overlaps the data load - the forward twin of what the inverse column pass does);
 //                   kPointwise = the point-wise product of a polynomial multiply before storing; or both
-enum TwistKind { kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2, kPointwise = 3, kPreTwist = 4, kPrePointwise = 5 };
+//   inverse rows  : kPostTwist = the mirror image: multiply by the matrix of the column pass that follows, before
+//                   storing (which also canonicalises); that column pass then runs twist-free
+enum TwistKind {
+  kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2, kPointwise = 3, kPreTwist = 4, kPrePointwise = 5, kPostTwist = 6
+};
 
 // the one place that decides (CUDA dispatcher and host emulator both call it)
 inline int pass_kind(bool col, bool inverse, bool map, const PassParams& prm) {
@@ -59,6 +63,7 @@ inline int pass_kind(bool col, bool inverse, bool map, const PassParams& prm) {
     if (prm.pre_twist != nullptr) return prm.pointwise != nullptr ? kPrePointwise : kPreTwist;
     if (prm.pointwise != nullptr) return kPointwise;
   }
+  if (inverse && !map && prm.pre_twist != nullptr) return kPostTwist;
   return kNoTwist;
 }
 
@@ -564,7 +569,11 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
       smem_load<Cfg, LOGS, R>(sm, k0, p, x);
     }
     inv_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, LOGS, i);
-    if constexpr (J == NS - 1) {
+    if constexpr (J == NS - 1 && TWIST == kPostTwist) {
+      // the twiddle matrix of the column pass behind this row pass (and 1/inverse_factor with it); canonical result
+      apply_pre_twist<F, Cfg, R>(f, prm, x, k0, LOGS, row0 + (u32)(p * Cfg::C));
+      gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
+    } else if constexpr (J == NS - 1) {
       if (prm.scale_on) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -653,6 +662,14 @@ __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_
   }
 #endif
   tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
+  if constexpr (TWIST == kPostTwist) {
+    // consumed by the last stage: start pulling this tile's rows of the matrix (16 N W bytes, contiguous per row)
+    // into L2 now
+    for (int i = threadIdx.x; i < Cfg::N * Cfg::W / 8; i += kThreads) {
+      const u32 row = row0 + (u32)(i >> (Cfg::LOGN - 3));
+      prefetch_l2(prm.pre_twist + (((u64)(row & prm.pre_rows_mask) << Cfg::LOGN) + (u64)(i & (Cfg::N / 8 - 1)) * 8));
+    }
+  }
   if constexpr (TWIST == kFullTwist && !INVERSE) {
     // forward: the twiddle matrix is consumed by the last stage - start pulling this tile's N segments of it
     // (W entries = 16 W bytes each) into L2 now, so that the streamed loads there do not wait for HBM

@@ -130,12 +130,13 @@ int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int
   return XNTT_OK;
 }
 
-// Forward only: the twiddle matrix of column pass i is applied by the row pass behind it, while that pass loads
-// its rows (contiguous, next to the data, at the start of a tile) instead of at the end of the column pass's tiles.
+// The twiddle matrix of column pass i is applied by the row pass next to it - forward while that pass loads its
+// rows, inverse before it stores them (contiguous rows of the matrix next to contiguous rows of data) - and the
+// column pass itself runs twist-free.
 // Holds for the last column pass whenever the planner stored its forward matrix (never for the column-sharded
 // first pass of a sharded plan).
-bool row_applies_twist(const xntt_plan* pl, size_t i) {
-  return i + 2 == pl->passes.size() && pl->passes[i].fwd_full != nullptr;
+bool row_applies_twist(const xntt_plan* pl, size_t i, bool inverse = false) {
+  return i + 2 == pl->passes.size() && (inverse ? pl->passes[i].inv_full : pl->passes[i].fwd_full) != nullptr;
 }
 
 // One pass.  `count_override` (when non-zero) replaces the number of outer blocks / rows: the row
@@ -164,7 +165,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.twist_shift = (u32)ps.twist_shift;
     prm.twist_full = inverse ? ps.inv_full : ps.fwd_full;
     prm.twist_full_shift = (u32)ps.log_inner;
-    if (!inverse && row_applies_twist(pl, i)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
+    if (row_applies_twist(pl, i, inverse)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
     prm.twist_col0 = sharded_first ? (u32)(inner * pl->shard_rank) : 0u;
     const u64 tiles = outer * prm.tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -175,8 +176,8 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.rows = (u32)rows;
     prm.scale_on = (inverse && pl->scale_on && pl->passes.size() == 1) ? 1u : 0u;
     prm.pointwise = inverse ? nullptr : pointwise;
-    if (!inverse && i > 0 && row_applies_twist(pl, i - 1)) {
-      prm.pre_twist = pl->passes[i - 1].fwd_full;
+    if (i > 0 && row_applies_twist(pl, i - 1, inverse)) {
+      prm.pre_twist = inverse ? pl->passes[i - 1].inv_full : pl->passes[i - 1].fwd_full;
       prm.pre_rows_mask = (1u << pl->passes[i - 1].logn) - 1u;
     }
     grid = (unsigned)((rows + (1u << logw) - 1) >> logw);
@@ -304,7 +305,7 @@ int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const
     prm.twist_shift = (u32)ps.twist_shift;
     prm.twist_full = inverse ? ps.inv_full : nullptr;  // forward: compact, or none when the row pass applies it
     prm.twist_full_shift = (u32)ps.log_inner;
-    if (!inverse && row_applies_twist(pl, i)) prm.twist_lo = prm.twist_hi = nullptr;
+    if (row_applies_twist(pl, i, inverse)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
     prm.twist_col0 = twist_col0;
     const u64 tiles = units * tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -444,10 +445,9 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   std::vector<char> use_ffull(q, 0), use_ifull(q, 0);
   // Whole-matrix twiddles (N * inner entries of 16 bytes per pass and direction: one modular product per residue
   // instead of two, no random table look-ups) while they fit the budget, outermost pass first, inverse before
-  // forward.  The inverse column pass consumes its matrix next to its tile loads; the forward matrix of the last
-  // column pass is consumed by the row pass the same way (row_applies_twist); only the forward matrix of an outer
-  // column pass of a three-pass plan is read at the end of that pass's tiles, which pays off while the matrix
-  // stays L2-resident (<= 64 MiB).  2^24: column pass 228 -> 180 us forward, 241 -> 228 us inverse.
+  // forward.  The matrices of the last column pass are applied by the row pass next to it (row_applies_twist); an
+  // outer column pass of a three-pass plan consumes its own, on load in the inverse and at the end of its tiles in
+  // the forward direction - the latter only pays off while the matrix stays L2-resident (<= 64 MiB).
   // Default budget 512 MiB per plan (both directions up to 2^24 cells); XNTT_TWIST_TABLE_MAX_MB overrides;
   // XNTT_COMPACT_TABLES and the column-sharded first pass of a sharded plan keep the compact two-table form.
   size_t full_budget = (size_t)512 << 20;

@@ -122,6 +122,7 @@ static int emu_launch2(const PassParams& prm, unsigned grid) {
       case kPointwise: emu_stages<F, Cfg, INV, kPointwise>(prm, sm.data(), gs, gd, col0, row0, seq); break;
       case kPreTwist: emu_stages<F, Cfg, INV, kPreTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
       case kPrePointwise: emu_stages<F, Cfg, INV, kPrePointwise>(prm, sm.data(), gs, gd, col0, row0, seq); break;
+      case kPostTwist: emu_stages<F, Cfg, INV, kPostTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
       default: emu_stages<F, Cfg, INV, kNoTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
     }
   }
