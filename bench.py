@@ -63,9 +63,9 @@ def measured_peaks():
 
 def ncu_traffic(workload, splits, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
-    ncu --set full capture of this very command (profiles/r1_v5_ncu_pass_kernels.json); None when the
+    ncu --set full capture of this very command (profiles/r1_v6_ncu_pass_kernels.json); None when the
     capture does not cover the configuration."""
-    path = os.path.join(ROOT, "profiles", "r1_v5_ncu_pass_kernels.json")
+    path = os.path.join(ROOT, "profiles", "r1_v6_ncu_pass_kernels.json")
     if workload != "ntt24" or list(splits) != [11, 13] or not os.path.exists(path):
         return None
     order = ["fwd_pass0_2^11", "fwd_pass1_2^13", "inv_pass1_2^13", "inv_pass0_2^11"]  # launch order in the capture

@@ -136,6 +136,10 @@ int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int
 // Holds for the last column pass whenever the planner stored its forward matrix (never for the column-sharded
 // first pass of a sharded plan).
 bool row_applies_twist(const xntt_plan* pl, size_t i, bool inverse = false) {
+  // Inverse of a plan sharded over 4 or more GPUs: column pass i is the one that stores its output into the peers'
+  // buffers and is bound by the links, not by arithmetic - the twiddle product is free there and would only lengthen
+  // the row pass (2^30 over 8 GPUs: inverse 4.38 vs 4.45 ms; over 2 GPUs the row pass wins, 2^28 3.91 vs 3.97 ms).
+  if (inverse && pl->shard_count >= 4) return false;
   return i + 2 == pl->passes.size() && (inverse ? pl->passes[i].inv_full : pl->passes[i].fwd_full) != nullptr;
 }
 
