@@ -54,6 +54,7 @@ struct xntt_plan {
   std::vector<PassDesc> passes;  // forward execution order; the last one is the row pass
   void* arena = nullptr;
   size_t arena_bytes = 0;
+  std::vector<void*> matrices;  // whole-matrix twiddles, one allocation each (a failed one falls back to compact)
   Tw scale{};  // Montgomery pair of inverse_factor^-1
   bool scale_on = false;
   u64 r2 = 0;  // 2^128 mod p
@@ -445,7 +446,6 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   pl->passes.resize(q);
   size_t words = 0;
   std::vector<size_t> off_fwd(q), off_inv(q), off_flo(q), off_fhi(q), off_ilo(q), off_ihi(q);
-  std::vector<size_t> off_ffull(q, 0), off_ifull(q, 0);
   std::vector<char> use_ffull(q, 0), use_ifull(q, 0);
   // Whole-matrix twiddles (N * inner entries of 16 bytes per pass and direction: one modular product per residue
   // instead of two, no random table look-ups) while they fit the budget, outermost pass first, inverse before
@@ -489,15 +489,11 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
         if (eligible && pl->inv && bytes <= full_budget) {
           full_budget -= bytes;
           use_ifull[i] = 1;
-          off_ifull[i] = words;
-          words += cells;
         }
         // forward: the last column pass (any plan), or an outer pass of an unsharded plan while it stays in L2
         if (eligible && pl->fwd && bytes <= full_budget && (i + 2 == q || (shard_count == 1 && bytes <= ((size_t)64 << 20)))) {
           full_budget -= bytes;
           use_ffull[i] = 1;
-          off_ffull[i] = words;
-          words += cells;
         }
       }
     }
@@ -536,15 +532,18 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
       // the outermost column pass runs last in the inverse: fold 1/inverse_factor into its table
       if (rc == XNTT_OK)
         rc = gen_table(pl->field, base + off_ihi[i], nhi, kPowers, 0, ps.twist_shift, root_big_inv, i == 0 ? finv : 1);
+      // the matrices get allocations of their own: if the device cannot spare one, that pass and direction simply
+      // keep the compact form
       const u32 cells = 1u << lm;
-      if (use_ffull[i] && rc == XNTT_OK) {
-        ps.fwd_full = base + off_ffull[i];
-        rc = gen_table(pl->field, base + off_ffull[i], cells, kTwist, ps.logn, ps.log_inner, root_big, 1);
-      }
-      if (use_ifull[i] && rc == XNTT_OK) {
-        ps.inv_full = base + off_ifull[i];
-        rc = gen_table(pl->field, base + off_ifull[i], cells, kTwist, ps.logn, ps.log_inner, root_big_inv,
-                       i == 0 ? finv : 1);
+      for (int dir = 0; dir < 2 && rc == XNTT_OK; ++dir) {
+        if (!(dir ? use_ifull[i] : use_ffull[i])) continue;
+        void* mem = nullptr;
+        if (be::dev_malloc(&mem, (size_t)cells * sizeof(Tw)) != 0) continue;
+        pl->matrices.push_back(mem);
+        Tw* t = static_cast<Tw*>(mem);
+        rc = gen_table(pl->field, t, cells, kTwist, ps.logn, ps.log_inner, dir ? root_big_inv : root_big,
+                       (dir && i == 0) ? finv : 1);
+        (dir ? ps.inv_full : ps.fwd_full) = t;
       }
     }
   }
@@ -554,6 +553,7 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   }
   if (rc != XNTT_OK) {
     be::dev_free(pl->arena);
+    for (void* mtx : pl->matrices) be::dev_free(mtx);
     delete pl;
     return rc;
   }
@@ -566,6 +566,7 @@ int xntt_plan_destroy(xntt_plan* pl) {
   {
     DeviceGuard g(pl->device);
     if (pl->arena) be::dev_free(pl->arena);
+    for (void* mtx : pl->matrices) be::dev_free(mtx);
     if (pl->staging) be::dev_free(pl->staging);
   }
   delete pl;
