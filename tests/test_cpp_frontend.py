@@ -46,3 +46,18 @@ def test_kinnaes_class_on_gpu():
     exe = _build("kinnaes_tests_gpu")
     out = subprocess.run([exe, "--all"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 12, out.stdout + out.stderr
+
+
+def test_magic_series_example_on_emulator():
+    """examples/magic-series (gaussian-polynomial.hpp drop-in): chunked power-series division through 2^15 NTT polynomial
+    multiplies; the reference's known answers m = 10 .. 100 over its eight moduli (test-magic-series.cpp:22-39, 315-325)."""
+    exe = _build("magic_series_tests_emu")
+    out = subprocess.run([exe, "--all"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 40, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_magic_series_example_on_gpu():
+    exe = _build("magic_series_tests_gpu")
+    out = subprocess.run([exe, "--all"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 40, out.stdout + out.stderr
