@@ -52,8 +52,48 @@ static void run_modulus(bool all) {
   }
 }
 
+// the helper classes on their own (test-magic-series.cpp: QPochhammer, RestrictedPartition, numerator segments)
+static void run_units() {
+  using modulus_type = sventt::Modulus<UINT64_C(0xffffffff00000001), 7>;
+  constexpr std::uint64_t N = modulus_type::get_modulus();
+  bool ok = true;
+  {  // (1-q)(1-q^2)(1-q^3) = 1 - q - q^2 + q^4 + q^5 - q^6
+    std::vector<std::uint64_t> c(7, 99);
+    calculate_q_pochhammer<modulus_type>(c, 3);
+    const std::vector<std::uint64_t> want{1, N - 1, N - 1, 0, 1, 1, N - 1};
+    ok = ok && c == want;
+  }
+  {  // partitions of n into parts <= 3: 1 1 2 3 4 5 7 8 10 12 14
+    RestrictedPartition<modulus_type> p(3);
+    const std::uint64_t want[] = {1, 1, 2, 3, 4, 5, 7, 8, 10, 12, 14};
+    for (std::uint64_t w : want) {
+      ok = ok && p() == w;
+      p.advance();
+    }
+    ok = ok && p.get_n() == 11 && p.get_k() == 3;
+  }
+  {  // [4 choose 2]_q = 1 + q + 2 q^2 + q^3 + q^4
+    GaussianPolynomialNumeratorSegment<modulus_type> seg(4);
+    seg.advance();  // [4 0]
+    seg.advance();  // [4 1]
+    seg.advance();  // [4 2]
+    ok = ok && seg.get_coefficients() == std::vector<std::uint64_t>{1, 1, 2, 1, 1};
+  }
+  {  // prod_{i=1..2} (1 - q^(5-2+i)) = (1 - q^4)(1 - q^5) = 1 - q^4 - q^5 + q^9, subtracted from zeros
+    GaussianPolynomialNumerator<modulus_type> num(5, 2);
+    std::vector<std::uint64_t> v(12, 0);
+    num.subtract_next(v.data(), 5);
+    num.subtract_next(v.data() + 5, 7);
+    const std::vector<std::uint64_t> want{N - 1, 0, 0, 0, 1, 1, 0, 0, 0, N - 1, 0, 0};
+    ok = ok && v == want;
+  }
+  std::printf("magic series helper classes %s\n", ok ? "ok" : "MISMATCH");
+  if (!ok) ++failures;
+}
+
 int main(int argc, char**) {
   const bool all = argc > 1;
+  run_units();
   run_modulus<UINT64_C(0xffffffff00000001), 7>(all);
   run_modulus<UINT64_C(0xa3b25f400c7a8001), 5>(all);
   if (all) {

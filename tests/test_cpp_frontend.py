@@ -53,11 +53,11 @@ def test_magic_series_example_on_emulator():
     multiplies; the reference's known answers m = 10 .. 100 over its eight moduli (test-magic-series.cpp:22-39, 315-325)."""
     exe = _build("magic_series_tests_emu")
     out = subprocess.run([exe, "--all"], capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 40, out.stdout + out.stderr
+    assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 41, out.stdout + out.stderr
 
 
 @pytest.mark.gpu
 def test_magic_series_example_on_gpu():
     exe = _build("magic_series_tests_gpu")
     out = subprocess.run([exe, "--all"], capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 40, out.stdout + out.stderr
+    assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 41, out.stdout + out.stderr
