@@ -1,5 +1,9 @@
 // SPDX-License-Identifier: Apache-2.0
-// Lab: candidate butterfly formulations (see bfly_lab.cu).
+// Lab: candidate butterfly formulations (see bfly_lab.cu).  Results on B200 (cycles per warp-butterfly at 1965 MHz, static
+// fma-pipe cycles in brackets): v0 = field.cuh at the start of the round 61.8 [55.2]; v8 = full low product instead of
+// IMAD.HI 60.6 [53.2] (adopted); v1 C-level conditionals 71.5; v3 PTX predicates 66.1; v4 canonical u + three fma repairs
+// 64.5; v5 plain C 71.3; v10 / v11 repairs on the ALU side: same static fma count as v9 (ptxas rebalances);
+// probes: no repairs 45.3-47.6, Montgomery product alone 49.2-50.4.
 #pragma once
 #include "field.cuh"
 
@@ -51,7 +55,8 @@ __device__ __forceinline__ void bf_v1(u64& x0, u64& x1, u64 w, u64 wp) {
   x1 = d;
 }
 
-// v2: canonical u, everything on carry flags + masks (LOP3)
+// v2: canonical u, everything on carry flags + masks (LOP3).  NOTE: this sketch returns wrong residues (the run on the
+// box flagged it, 65.4 cycles anyway) and is not part of main(); kept only as the record of what was timed.
 __device__ __forceinline__ void bf_v2(u64& x0, u64& x1, u64 w, u64 wp) {
   u64 u;
   u32 m;
