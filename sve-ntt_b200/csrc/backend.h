@@ -20,6 +20,13 @@ int host_free_pinned(void* p);
 int memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
 int memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
 int stream_sync(void* stream);
+// streams and events for the chunk pipeline behind the host entry points of batched plans
+int stream_create(void** stream);
+int stream_destroy(void* stream);
+int event_create(void** event);
+int event_destroy(void* event);
+int event_record(void* event, void* stream);
+int stream_wait_event(void* stream, void* event);
 int pointer_is_device(const void* p, int* is_device);
 const char* last_error();
 

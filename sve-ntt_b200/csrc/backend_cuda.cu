@@ -193,6 +193,34 @@ int stream_sync(void* st) {
   CU(cudaStreamSynchronize((cudaStream_t)st));
   return 0;
 }
+int stream_create(void** st) {
+  cudaStream_t s;
+  CU(cudaStreamCreate(&s));  // blocking stream: ordered against the legacy default stream the plain path uses
+  *st = s;
+  return 0;
+}
+int stream_destroy(void* st) {
+  CU(cudaStreamDestroy((cudaStream_t)st));
+  return 0;
+}
+int event_create(void** ev) {
+  cudaEvent_t e;
+  CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *ev = e;
+  return 0;
+}
+int event_destroy(void* ev) {
+  CU(cudaEventDestroy((cudaEvent_t)ev));
+  return 0;
+}
+int event_record(void* ev, void* st) {
+  CU(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st));
+  return 0;
+}
+int stream_wait_event(void* st, void* ev) {
+  CU(cudaStreamWaitEvent((cudaStream_t)st, (cudaEvent_t)ev, 0));
+  return 0;
+}
 int pointer_is_device(const void* p, int* is_device) {
   cudaPointerAttributes a;
   cudaError_t e = cudaPointerGetAttributes(&a, p);

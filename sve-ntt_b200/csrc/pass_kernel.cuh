@@ -665,9 +665,9 @@ __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_
   if constexpr (TWIST == kPostTwist) {
     // consumed by the last stage: start pulling this tile's rows of the matrix (16 N W bytes, contiguous per row)
     // into L2 now
-    for (int i = threadIdx.x; i < Cfg::N * Cfg::W / 8; i += kThreads) {
-      const u32 row = row0 + (u32)(i >> (Cfg::LOGN - 3));
-      prefetch_l2(prm.pre_twist + (((u64)(row & prm.pre_rows_mask) << Cfg::LOGN) + (u64)(i & (Cfg::N / 8 - 1)) * 8));
+    for (int e = threadIdx.x * 8; e < Cfg::N * Cfg::W; e += kThreads * 8) {  // one 128-byte line = 8 entries
+      const u32 row = row0 + (u32)(e >> Cfg::LOGN);
+      prefetch_l2(prm.pre_twist + (((u64)(row & prm.pre_rows_mask) << Cfg::LOGN) + (u64)(e & (Cfg::N - 1))));
     }
   }
   if constexpr (TWIST == kFullTwist && !INVERSE) {

@@ -61,6 +61,9 @@ struct xntt_plan {
   u32 shard_count = 1, shard_rank = 0;
   FieldConsts field{};
   mutable void* staging = nullptr;  // device buffer behind the *_host entry points (lazy)
+  // chunk pipeline of the host entry points of batched plans (lazy): copy-in, compute, copy-out streams + events
+  mutable void* pipe_streams[3] = {nullptr, nullptr, nullptr};
+  mutable std::vector<void*> pipe_events;
 };
 
 namespace {
@@ -194,7 +197,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
 // passes [first, last) in forward order (reverse order for the inverse); the first executed pass
 // reads src, every later one works in place on dst.
 int run_range(const xntt_plan* pl, bool inverse, size_t first, size_t last, u64* dst, const u64* src, void* st,
-              bool shard_rows, const u64* pointwise = nullptr) {
+              bool shard_rows, const u64* pointwise = nullptr, u32 batch_override = 0) {
   if (!dst || !src) return XNTT_ERR_INVALID;
   if (inverse ? !pl->inv : !pl->fwd) return XNTT_ERR_STATE;
   DeviceGuard g(pl->device);
@@ -203,7 +206,10 @@ int run_range(const xntt_plan* pl, bool inverse, size_t first, size_t last, u64*
   for (size_t s = 0; s < last - first; ++s) {
     const size_t i = inverse ? last - 1 - s : first + s;
     u64 count = 0;
-    if (shard_rows) {
+    if (batch_override) {  // a chunk of the plan's batch (host pipeline)
+      const PassDesc& ps = pl->passes[i];
+      count = ps.col ? ((u64)batch_override << ps.log_outer) : ((u64)batch_override << (pl->log2_m - ps.logn));
+    } else if (shard_rows) {
       const PassDesc& ps = pl->passes[i];
       const u64 full = ps.col ? ((u64)pl->batch << ps.log_outer) : ((u64)pl->batch << (pl->log2_m - ps.logn));
       count = full / pl->shard_count;
@@ -215,14 +221,55 @@ int run_range(const xntt_plan* pl, bool inverse, size_t first, size_t last, u64*
   return XNTT_OK;
 }
 
+// Batched plans: the transforms are independent, so the batch is cut into chunks that flow through three streams -
+// copy in, transform, copy out - and the two DMA directions of the link run at the same time.  (One transform
+// cannot do that: its last pass needs every word of its first.)
+int host_pipeline(const xntt_plan* pl, u64* d, uint64_t* dst, const uint64_t* src, bool inverse, u32 chunks) {
+  const size_t words = (size_t)1 << pl->log2_m;
+  const u32 per = (pl->batch + chunks - 1) / chunks;
+  if (!pl->pipe_streams[0])
+    for (int i = 0; i < 3; ++i) BE(be::stream_create(&pl->pipe_streams[i]));
+  while (pl->pipe_events.size() < 2 * (size_t)chunks) {
+    void* ev = nullptr;
+    BE(be::event_create(&ev));
+    pl->pipe_events.push_back(ev);
+  }
+  void *s_in = pl->pipe_streams[0], *s_run = pl->pipe_streams[1], *s_out = pl->pipe_streams[2];
+  const size_t q = pl->passes.size();
+  for (u32 i = 0, b0 = 0; b0 < pl->batch; ++i, b0 += per) {
+    const u32 nb = pl->batch - b0 < per ? pl->batch - b0 : per;
+    const size_t off = (size_t)b0 * words, bytes = (size_t)nb * words * sizeof(u64);
+    BE(be::memcpy_h2d(d + off, src + off, bytes, s_in));
+    BE(be::event_record(pl->pipe_events[2 * i], s_in));
+    BE(be::stream_wait_event(s_run, pl->pipe_events[2 * i]));
+    const int rc = run_range(pl, inverse, 0, q, d + off, d + off, s_run, false, nullptr, nb);
+    if (rc != XNTT_OK) return rc;
+    BE(be::event_record(pl->pipe_events[2 * i + 1], s_run));
+    BE(be::stream_wait_event(s_out, pl->pipe_events[2 * i + 1]));
+    BE(be::memcpy_d2h(dst + off, d + off, bytes, s_out));
+  }
+  BE(be::stream_sync(s_out));
+  BE(be::stream_sync(s_run));
+  return XNTT_OK;
+}
+
 int host_roundtrip(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, bool inverse) {
   if (!pl || !dst || !src) return XNTT_ERR_INVALID;
   if (pl->shard_count > 1) return XNTT_ERR_STATE;
+  if (inverse ? !pl->inv : !pl->fwd) return XNTT_ERR_STATE;
   DeviceGuard g(pl->device);
   if (!g.ok) return be_fail(1);
   const size_t bytes = (sizeof(u64) << pl->log2_m) * pl->batch;
   if (!pl->staging) BE(be::dev_malloc(&pl->staging, bytes));
   void* d = pl->staging;
+  // chunks of at least 8 MiB (below that the copies are latency-bound), at most 8 of them
+  u32 chunks = 1;
+  while (chunks < 8 && chunks * 2 <= pl->batch && bytes / (chunks * 2) >= ((size_t)8 << 20)) chunks *= 2;
+  if (chunks > 1) {
+    const int prc = host_pipeline(pl, (u64*)d, dst, src, inverse, chunks);
+    if (prc != XNTT_OK) be::stream_sync(nullptr);
+    return prc;
+  }
   int rc = XNTT_OK, brc;
   if ((brc = be::memcpy_h2d(d, src, bytes, nullptr)) != 0) rc = be_fail(brc);
   if (rc == XNTT_OK) rc = run_range(pl, inverse, 0, pl->passes.size(), (u64*)d, (const u64*)d, nullptr, false);
@@ -568,6 +615,9 @@ int xntt_plan_destroy(xntt_plan* pl) {
     if (pl->arena) be::dev_free(pl->arena);
     for (void* mtx : pl->matrices) be::dev_free(mtx);
     if (pl->staging) be::dev_free(pl->staging);
+    for (void* ev : pl->pipe_events) be::event_destroy(ev);
+    for (void* st : pl->pipe_streams)
+      if (st) be::stream_destroy(st);
   }
   delete pl;
   return XNTT_OK;

@@ -182,6 +182,19 @@ int memcpy_d2h(void* dst, const void* src, size_t bytes, void*) {
   return 0;
 }
 int stream_sync(void*) { return 0; }
+// the emulator executes every "launch" and copy at once, in program order: streams and events are tokens
+int stream_create(void** st) {
+  *st = nullptr;
+  return 0;
+}
+int stream_destroy(void*) { return 0; }
+int event_create(void** ev) {
+  *ev = nullptr;
+  return 0;
+}
+int event_destroy(void*) { return 0; }
+int event_record(void*, void*) { return 0; }
+int stream_wait_event(void*, void*) { return 0; }
 int pointer_is_device(const void*, int* is_device) {
   *is_device = 0;
   return 0;
