@@ -150,7 +150,7 @@ bool row_applies_twist(const xntt_plan* pl, size_t i, bool inverse = false) {
 // One pass.  `count_override` (when non-zero) replaces the number of outer blocks / rows: the row
 // half of a sharded plan only holds 1/shard_count of them.
 int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* src, void* st,
-             u64 count_override, const u64* pointwise = nullptr) {
+             u64 count_override, const u64* pointwise = nullptr, u64 chunk_row0 = 0) {
   const PassDesc& ps = pl->passes[i];
   PassParams prm{};
   prm.src = src;
@@ -187,6 +187,9 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     if (i > 0 && row_applies_twist(pl, i - 1, inverse)) {
       prm.pre_twist = inverse ? pl->passes[i - 1].inv_full : pl->passes[i - 1].fwd_full;
       prm.pre_rows_mask = (1u << pl->passes[i - 1].logn) - 1u;
+      // a row chunk (host pipeline): power-of-two chunks are either whole multiples of the matrix height or lie
+      // inside one copy of it, so the rows before the chunk turn into a pointer offset
+      prm.pre_twist += (chunk_row0 & prm.pre_rows_mask) << ps.logn;
     }
     grid = (unsigned)((rows + (1u << logw) - 1) >> logw);
   }
@@ -253,6 +256,52 @@ int host_pipeline(const xntt_plan* pl, u64* d, uint64_t* dst, const uint64_t* sr
   return XNTT_OK;
 }
 
+// One large transform (or a batch too small to cut): only the row pass - contiguous rows - can overlap a copy.
+// Forward: copy in, column passes, then the row pass in row chunks, each followed by its copy out; inverse: the
+// row pass of a chunk as soon as its rows have arrived, then the column passes and one copy out.
+int host_row_pipeline(const xntt_plan* pl, u64* d, uint64_t* dst, const uint64_t* src, bool inverse, u32 chunks) {
+  const size_t q = pl->passes.size(), last = q - 1;
+  const PassDesc& rp = pl->passes[last];
+  const u64 rows = (u64)pl->batch << (pl->log2_m - rp.logn);
+  while (chunks > 1 && (rows % chunks != 0 || (rows / chunks) % (1u << tile_logw(rp.logn)) != 0)) chunks /= 2;
+  const u64 per = rows / chunks;
+  const size_t chunk_words = (size_t)per << rp.logn, chunk_bytes = chunk_words * sizeof(u64);
+  const size_t bytes = (sizeof(u64) << pl->log2_m) * pl->batch;
+  if (!pl->pipe_streams[0])
+    for (int i = 0; i < 3; ++i) BE(be::stream_create(&pl->pipe_streams[i]));
+  while (pl->pipe_events.size() < 2 * (size_t)chunks) {
+    void* ev = nullptr;
+    BE(be::event_create(&ev));
+    pl->pipe_events.push_back(ev);
+  }
+  void *s_in = pl->pipe_streams[0], *s_run = pl->pipe_streams[1], *s_out = pl->pipe_streams[2];
+  int rc;
+  if (!inverse) {
+    BE(be::memcpy_h2d(d, src, bytes, s_run));
+    if (q > 1 && (rc = run_range(pl, false, 0, last, d, d, s_run, false)) != XNTT_OK) return rc;
+    for (u32 i = 0; i < chunks; ++i) {
+      const size_t off = (size_t)i * chunk_words;
+      if ((rc = run_pass(pl, last, false, d + off, d + off, s_run, per, nullptr, (u64)i * per)) != XNTT_OK) return rc;
+      BE(be::event_record(pl->pipe_events[i], s_run));
+      BE(be::stream_wait_event(s_out, pl->pipe_events[i]));
+      BE(be::memcpy_d2h(dst + off, d + off, chunk_bytes, s_out));
+    }
+    BE(be::stream_sync(s_out));
+  } else {
+    for (u32 i = 0; i < chunks; ++i) {
+      const size_t off = (size_t)i * chunk_words;
+      BE(be::memcpy_h2d(d + off, src + off, chunk_bytes, s_in));
+      BE(be::event_record(pl->pipe_events[i], s_in));
+      BE(be::stream_wait_event(s_run, pl->pipe_events[i]));
+      if ((rc = run_pass(pl, last, true, d + off, d + off, s_run, per, nullptr, (u64)i * per)) != XNTT_OK) return rc;
+    }
+    if (q > 1 && (rc = run_range(pl, true, 0, last, d, d, s_run, false)) != XNTT_OK) return rc;
+    BE(be::memcpy_d2h(dst, d, bytes, s_run));
+  }
+  BE(be::stream_sync(s_run));
+  return XNTT_OK;
+}
+
 int host_roundtrip(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, bool inverse) {
   if (!pl || !dst || !src) return XNTT_ERR_INVALID;
   if (pl->shard_count > 1) return XNTT_ERR_STATE;
@@ -267,6 +316,11 @@ int host_roundtrip(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, bool
   while (chunks < 8 && chunks * 2 <= pl->batch && bytes / (chunks * 2) >= ((size_t)8 << 20)) chunks *= 2;
   if (chunks > 1) {
     const int prc = host_pipeline(pl, (u64*)d, dst, src, inverse, chunks);
+    if (prc != XNTT_OK) be::stream_sync(nullptr);
+    return prc;
+  }
+  if (bytes >= ((size_t)32 << 20)) {
+    const int prc = host_row_pipeline(pl, (u64*)d, dst, src, inverse, 8);
     if (prc != XNTT_OK) be::stream_sync(nullptr);
     return prc;
   }
