@@ -204,11 +204,12 @@ def test_host_entry_points(cuda_lib, oracle):
     plan.close()
 
 
-@pytest.mark.parametrize("L,batch", [(16, 1), (12, 5), (20, 2), (9, 3), (18, 37)])
+@pytest.mark.parametrize("L,batch", [(16, 1), (12, 5), (20, 2), (9, 3), (18, 37), (22, 1)])
 def test_host_entry_points_page_locked(cuda_lib, oracle, L, batch):
     """Page-locked host buffers (what bench.py's e2e leg and sventt::PageMemory hand in): same words as the
     pageable route, also in place, batched (large batches flow through the copy / transform / copy chunk pipeline,
-    here 37 x 2^18 = 8 ragged chunks) and for single-pass plans."""
+    here 37 x 2^18 = 8 ragged chunks; one 2^22 transform has its row pass cut into chunks that overlap the copies) and
+    for single-pass plans."""
     import torch
     m = 1 << L
     a = oracle.fill_xorshift(m * batch, SEED + L, P0)
