@@ -371,3 +371,23 @@ def test_transpose_contract(emu):
         b = a.copy()
         emu.transpose(b.ctypes.data, b.ctypes.data, dim, dim, dim + pad, dim + pad)
         assert np.array_equal(b[:, :dim], a[:, :dim].T)
+
+
+@pytest.mark.parametrize("L,batch,splits", [(20, 5, None), (16, 200, None), (22, 1, None), (22, 1, [7, 7, 8])])
+def test_host_entry_point_pipelines(emu, oracle, L, batch, splits):
+    """xntt_forward_host / xntt_inverse_host on buffers large enough for the chunk pipelines: a batch cut into
+    (ragged) chunks of transforms, and one transform whose row pass runs in row chunks (twiddle-matrix rows offset
+    per chunk).  The emulator executes streams in program order, so this checks the chunk index algebra."""
+    m = 1 << L
+    a = oracle.fill_xorshift(m * batch, SEED + 3 * L, P0)
+    plan = emu.plan(L, batch=batch, splits=splits, inverse_factor=5)
+    out, back = np.empty_like(a), np.empty_like(a)
+    plan.forward_host(out.ctypes.data, a.ctypes.data)
+    for b in sorted({0, batch // 2, batch - 1}):
+        assert np.array_equal(out[b * m:(b + 1) * m], oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), P0, G0)), b
+    plan.inverse_host(back.ctypes.data, out.ctypes.data)
+    scale = np.full_like(a, (m * pow(5, -1, P0)) % P0)
+    assert np.array_equal(back, oracle.pointwise_mul(a, scale, P0))
+    # in place
+    plan.forward_host(a.ctypes.data, a.ctypes.data)
+    assert np.array_equal(a, out)
