@@ -467,10 +467,6 @@ __device__ __forceinline__ void stage_barrier() {
   }
 #endif
 }
-#ifndef XNTT_TASK_UNROLL
-#define XNTT_TASK_UNROLL 1
-#endif
-constexpr int kTaskUnroll = XNTT_TASK_UNROLL;  // tasks of one stage a thread works on at a time
 
 // ---------------------------------------------------------------------------------------------
 template <class F, class Cfg, int TWIST, int J>
@@ -483,7 +479,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
   constexpr int LOGS = Cfg::LOGRN * (NS - 1 - J);
   constexpr int LOGT = Cfg::LOGN - LOGR;  // tasks per sub-transform
   constexpr int NTASK = (1 << LOGT) * Cfg::NP;
-#pragma unroll(kTaskUnroll)
+#pragma unroll 1
   for (int task = threadIdx.x; task < NTASK; task += kThreads) {
     int p, t;
     if constexpr (Cfg::COL) {
@@ -548,7 +544,7 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
   constexpr int LOGS = Cfg::LOGRN * J;
   constexpr int LOGT = Cfg::LOGN - LOGR;
   constexpr int NTASK = (1 << LOGT) * Cfg::NP;
-#pragma unroll(kTaskUnroll)
+#pragma unroll 1
   for (int task = threadIdx.x; task < NTASK; task += kThreads) {
     int p, t;
     if constexpr (Cfg::COL) {
@@ -628,11 +624,6 @@ __device__ __forceinline__ void tile_origin(const PassParams& prm, u32 tile, u64
 }
 
 #if !defined(XNTT_HOST_EMU)
-// Distance (in tiles) of the L2 prefetch each CTA issues for a tile that will start soon (0 = off).
-#ifndef XNTT_PREFETCH_TILE
-#define XNTT_PREFETCH_TILE 0
-#endif
-
 template <class F, int LOGN, int LOGW, int C, bool COL, bool INVERSE, int TWIST, bool MAP = false>
 __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_constant__ PassParams prm) {
   typedef PassCfg<LOGN, LOGW, C, COL, MAP> Cfg;
@@ -641,26 +632,6 @@ __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_
   const u32 tile = blockIdx.x;
   u64 sbase, dbase;
   u32 col0 = 0, row0 = 0;
-#if XNTT_PREFETCH_TILE > 0
-  if constexpr (!MAP) {
-    const u32 nt = tile + XNTT_PREFETCH_TILE;
-    if (nt < gridDim.x) {
-      u64 sb, db;
-      u32 c0 = 0, r0 = 0;
-      tile_origin<Cfg>(prm, nt, sb, db, c0, r0);
-      const u64* q = prm.src + sb;
-      if constexpr (COL) {
-        // N row segments of W words each
-        for (int k = threadIdx.x; k < Cfg::N; k += kThreads)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (u64)k * prm.inner));
-      } else {
-        // contiguous: one 128-byte line per prefetch
-        for (int l = threadIdx.x; l < (Cfg::N * Cfg::W) / 16; l += kThreads)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (u64)l * 16));
-      }
-    }
-  }
-#endif
   tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
   if constexpr (TWIST == kPostTwist) {
     // consumed by the last stage: start pulling this tile's rows of the matrix (16 N W bytes, contiguous per row)
