@@ -140,6 +140,7 @@ def reference_arm(args, rank, world):
     total = args.steps + args.warmup
     # one step of NTTReference at 2^24 costs ~14 s: shrink the sample so the run ends in minutes
     log2_n = 24 if total <= 8 else (22 if total <= 40 else 20)
+    log2_n = int(os.environ.get("XNTT_BENCH_REF_LOG2", log2_n))  # tests shrink the sample
     n = 1 << log2_n
     # the class is serial; what shards over N GPUs on our side (one independent transform per GPU) runs here as N
     # independent transforms on N host threads (ctypes releases the GIL) - all the threads this workload can use
