@@ -67,6 +67,10 @@ typedef struct xntt_desc {
   /* [shard_rank * n1 / shard_count, ...) of the first split's n0 x n1 matrix. 0/0 = not sharded.   */
   uint32_t shard_count;
   uint32_t shard_rank;
+  /* budget for whole twiddle matrices (16 bytes per residue and direction), MiB per plan; 0 = default (512).  */
+  /* A matrix that does not fit keeps the compact two-table form; XNTT_COMPACT_TABLES forces that everywhere. */
+  uint32_t twist_table_max_mb;
+  uint32_t reserved_;
 } xntt_desc;
 
 typedef struct xntt_plan xntt_plan;
@@ -178,6 +182,10 @@ int xntt_transpose(uint64_t* dst, const uint64_t* src, uint64_t rows, uint64_t c
 int xntt_kinnaes_sum(uint64_t modulus, uint64_t generator, uint64_t m, uint64_t n, uint64_t j_begin, uint64_t j_end,
                      int device, uint64_t* result);
 int xntt_kinnaes_compute(uint64_t modulus, uint64_t generator, uint64_t m, uint64_t n, int device, uint64_t* result);
+
+/* Frees the per-device result buffers the Kinnaes entry points keep between calls (a cudaMalloc / cudaFree pair per
+ * call would cost thirty times the kernel).  Call before cudaDeviceReset / at unload; later calls re-create them. */
+int xntt_release_scratch(void);
 
 /* Device-resident PageMemory twin (include/sventt/vector.hpp:61-168): pinned host memory for the
  * host entry points / device memory for the device ones. */

@@ -40,6 +40,8 @@ class Desc(C.Structure):
         ("split_log2", C.c_uint32 * MAX_SPLITS),
         ("shard_count", C.c_uint32),
         ("shard_rank", C.c_uint32),
+        ("twist_table_max_mb", C.c_uint32),
+        ("reserved_", C.c_uint32),
     ]
 
 
@@ -88,6 +90,7 @@ SYMBOLS = {
     "xntt_kinnaes_sum": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
                                  C.POINTER(C.c_uint64)]),
     "xntt_kinnaes_compute": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
+    "xntt_release_scratch": (C.c_int, []),
     "xntt_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -151,7 +154,7 @@ class Plan:
 
     def __init__(self, library, log2_m, modulus=P0, generator=G0, batch=1, inverse_factor=None,
                  forward=True, inverse=True, device=-1, splits=None, shard_count=0, shard_rank=0,
-                 compact_tables=False):
+                 compact_tables=False, twist_table_max_mb=0):
         self.L = library
         d = Desc()
         d.modulus, d.generator = modulus, generator
@@ -165,6 +168,7 @@ class Plan:
             for i, s in enumerate(splits):
                 d.split_log2[i] = s
         d.shard_count, d.shard_rank = shard_count, shard_rank
+        d.twist_table_max_mb = twist_table_max_mb
         self.desc = d
         self.h = C.c_void_p()
         library.check(library.lib.xntt_plan_create(C.byref(self.h), C.byref(d)), "xntt_plan_create")

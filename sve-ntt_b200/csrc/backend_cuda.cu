@@ -314,16 +314,18 @@ int launch_mulnorm(const FieldConsts& fc, u64* dst, const u64* a, const u64* b, 
 int launch_transpose(u64* dst, const u64* src, u64 rows, u64 cols, u64 ld_dst, u64 ld_src, void* stream) {
   TransposeParams p{dst, src, rows, cols, ld_dst, ld_src, (u32)((cols + kTrTile - 1) / kTrTile)};
   const u64 tiles_r = (rows + kTrTile - 1) / kTrTile;
-  static bool attr_done_on[64] = {};  // per device, like the pass kernels (dispatch.cuh)
+  static std::atomic<bool> attr_done_on[64];  // per device, like the pass kernels (dispatch.cuh)
+  static std::mutex attr_mu;
   int dev = 0;
   CU(cudaGetDevice(&dev));
-  bool& attr_done = attr_done_on[dev & 63];
-  if (!attr_done) {
+  std::atomic<bool>& attr_done = attr_done_on[dev & 63];
+  if (!attr_done.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lock(attr_mu);
     CU(cudaFuncSetAttribute(transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(kTrSmemWords * sizeof(u64))));
     CU(cudaFuncSetAttribute(transpose_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(2 * kTrSmemWords * sizeof(u64))));
-    attr_done = true;
+    attr_done.store(true, std::memory_order_release);
   }
   if (dst == src) {
     const dim3 grid2(p.tiles_c, p.tiles_c);

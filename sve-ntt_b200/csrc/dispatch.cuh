@@ -2,6 +2,9 @@
 // Launch-side view of the pass kernels: the dispatchers (one translation unit per direction / mode
 // / field flavour so the heavy template instantiations compile in parallel).
 #pragma once
+#include <atomic>
+#include <mutex>
+
 #include "pass_kernel.cuh"
 
 namespace xntt {
@@ -26,13 +29,17 @@ cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st)
   constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
   auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, TWIST, MAP>;
-  // function attributes live in the context of the device they were set on: once per kernel and device
-  static bool attr_done_on[64] = {};
+  // function attributes live in the context of the device they were set on: once per kernel and device, and
+  // safe against two host threads launching the same kernel for the first time (the reference's compute_* are
+  // const and re-entrant, wrapper.hpp:50-82)
+  static std::atomic<bool> attr_done_on[64];
+  static std::mutex attr_mu;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  bool& attr_done = attr_done_on[dev & 63];
-  if (!attr_done) {
+  std::atomic<bool>& attr_done = attr_done_on[dev & 63];
+  if (!attr_done.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lock(attr_mu);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
 #ifndef XNTT_CARVE_TILES
@@ -45,7 +52,7 @@ cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st)
                              (int)((XNTT_CARVE_TILES * (Cfg::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
     if (e != cudaSuccess) return e;
 #endif
-    attr_done = true;
+    attr_done.store(true, std::memory_order_release);
   }
   kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(prm);
   return cudaGetLastError();

@@ -76,11 +76,13 @@ struct PassParams {
   Tw scale;
   FieldConsts field;
   StrideMap smap, dmap;  // MAP kernels only: address maps of src and dst
-  // MAP kernels only, peer_bits != 0: output word with transform index k is stored through
+  // MAP kernels only, peer_on != 0: output word with transform index k is stored through
   // peer[k >> peer_bits] (another GPU's buffer, mapped over NVLink) at dmap(k & (2^peer_bits - 1)) -
   // the all-to-all of a sharded transform fused into the pass that produces the data
+  // (peer_bits == 0 is a legal value: every k of the pass belongs to another rank)
   u64* peer[8];
   u32 peer_bits;
+  u32 peer_on;
   const u64* pointwise;  // forward row pass: multiply output word i by pointwise[i] * 2^-64 (fused
                          // PAdic64::multiply_normalize against a to_montgomery'd spectrum), or null
 };

@@ -244,7 +244,7 @@ template <class Cfg, int R>
 __device__ __forceinline__ void gmem_store(const PassParams& prm, u64* base, u32 row0, int k0, int logs, int p,
                                            const u64 (&x)[R][Cfg::C]) {
   if constexpr (Cfg::MAP) {
-    if (prm.peer_bits != 0) {
+    if (prm.peer_on != 0) {
       // fused exchange: the owner of output index k is rank k >> peer_bits; all ranks' buffers share one
       // layout, so the tile offset (base - prm.dst) carries over
       const u64 tile_ofs = (u64)(base - prm.dst);

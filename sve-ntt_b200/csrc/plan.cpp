@@ -60,6 +60,9 @@ struct xntt_plan {
   u64 r2 = 0;  // 2^128 mod p
   u32 shard_count = 1, shard_rank = 0;
   FieldConsts field{};
+  // The *_host entry points own lazily created state (staging buffer, pipeline streams and events): they are
+  // serialised on this mutex, so a plan may be shared by host threads; the device entry points touch no plan state.
+  mutable std::mutex host_mu;
   mutable void* staging = nullptr;  // device buffer behind the *_host entry points (lazy)
   // chunk pipeline of the host entry points of batched plans (lazy): copy-in, compute, copy-out streams + events
   mutable void* pipe_streams[3] = {nullptr, nullptr, nullptr};
@@ -308,6 +311,7 @@ int host_roundtrip(const xntt_plan* pl, uint64_t* dst, const uint64_t* src, bool
   if (inverse ? !pl->inv : !pl->fwd) return XNTT_ERR_STATE;
   DeviceGuard g(pl->device);
   if (!g.ok) return be_fail(1);
+  std::lock_guard<std::mutex> host_lock(pl->host_mu);
   const size_t bytes = (sizeof(u64) << pl->log2_m) * pl->batch;
   if (!pl->staging) BE(be::dev_malloc(&pl->staging, bytes));
   void* d = pl->staging;
@@ -400,6 +404,7 @@ int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const
   if (peers) {
     for (u32 s = 0; s < pl->shard_count; ++s) prm.peer[s] = peers[s] + peer_offset;
     prm.peer_bits = peer_bits;
+    prm.peer_on = 1;
     prm.dst = peers[pl->shard_rank] + peer_offset;  // tile offsets are taken relative to prm.dst
   }
   const int logw = tile_logw(ps.logn);
@@ -553,10 +558,9 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   // forward.  The matrices of the last column pass are applied by the row pass next to it (row_applies_twist); an
   // outer column pass of a three-pass plan consumes its own, on load in the inverse and at the end of its tiles in
   // the forward direction - the latter only pays off while the matrix stays L2-resident (<= 64 MiB).
-  // Default budget 512 MiB per plan (both directions up to 2^24 cells); XNTT_TWIST_TABLE_MAX_MB overrides;
+  // Default budget 512 MiB per plan (both directions up to 2^24 cells); xntt_desc::twist_table_max_mb overrides;
   // XNTT_COMPACT_TABLES and the column-sharded first pass of a sharded plan keep the compact two-table form.
-  size_t full_budget = (size_t)512 << 20;
-  if (const char* e = std::getenv("XNTT_TWIST_TABLE_MAX_MB")) full_budget = (size_t)std::strtoull(e, nullptr, 10) << 20;
+  size_t full_budget = (size_t)(d->twist_table_max_mb ? d->twist_table_max_mb : 512u) << 20;
   if (d->flags & XNTT_COMPACT_TABLES) full_budget = 0;
   {
     int rem = pl->log2_m, before = 0;
@@ -949,10 +953,16 @@ int xntt_device_count(void) {
 
 // ---- Kinnaes' formula (examples/magic-series-kinnaes/kinnaes.hpp) --------------------------------------------
 namespace {
+// one small result buffer per device, created on first use, released by xntt_release_scratch()
+std::mutex g_kinnaes_mu;
+void* g_kinnaes_scratch[64] = {};
+
 int kinnaes_sum_impl(u64 p, u64 gen, u64 m, u64 n, u64 j_begin, u64 j_end, int device, u64* result) {
   if ((p & 1) == 0 || p < 3 || gen == 0 || !h_is_prime(p)) return XNTT_ERR_INVALID;
   if (m < 2 || m >= (1ull << 20) || n == 0 || (p - 1) % n != 0) return XNTT_ERR_INVALID;
   if (j_begin > j_end || j_end > n / 2) return XNTT_ERR_INVALID;
+  // the kernel builds w^J from ladder[i] = w^(2^i), i < kKinnaesLadder: J must fit
+  if (j_end >> kKinnaesLadder) return XNTT_ERR_INVALID;
   *result = 0;
   if (j_begin == j_end) return XNTT_OK;  // empty sum: 0 / 1
   int dev = device;
@@ -977,10 +987,9 @@ int kinnaes_sum_impl(u64 p, u64 gen, u64 m, u64 n, u64 j_begin, u64 j_end, int d
   if (blocks > kKinnaesMaxBlocks) blocks = kKinnaesMaxBlocks;
   // one small result buffer per device, kept for the life of the process (a cudaMalloc / cudaFree pair per call
   // costs 5-7 ms, thirty times the kernel); calls are serialised on it
-  static std::mutex mu;
-  static void* scratch[64] = {};
   if (dev >= 64) return XNTT_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(mu);
+  std::lock_guard<std::mutex> lock(g_kinnaes_mu);
+  void** scratch = g_kinnaes_scratch;
   if (!scratch[dev]) BE(be::dev_malloc(&scratch[dev], kKinnaesMaxBlocks * 2 * sizeof(u64)));
   void* dpart = scratch[dev];
   prm.partial = static_cast<u64*>(dpart);
@@ -1027,6 +1036,18 @@ int xntt_kinnaes_compute(uint64_t modulus, uint64_t generator, uint64_t m, uint6
   sum = (u64)(((u128)sum + h_mul(num, h_inv(den, p), p)) % p);
   *result = h_mul(sum, h_inv(n % p, p), p);
   return XNTT_OK;
+}
+
+int xntt_release_scratch(void) {
+  std::lock_guard<std::mutex> lock(g_kinnaes_mu);
+  int rc = XNTT_OK;
+  for (int dev = 0; dev < 64; ++dev) {
+    if (!g_kinnaes_scratch[dev]) continue;
+    DeviceGuard g(dev);
+    if (!g.ok || be::dev_free(g_kinnaes_scratch[dev]) != 0) rc = be_fail(1);
+    g_kinnaes_scratch[dev] = nullptr;
+  }
+  return rc;
 }
 
 int xntt_microbench(int kind, int iters, double* gops, double* ms) {

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libntt_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libnttref.so")
+REF_SCALAR_SO = os.path.join(ORACLE_DIR, "_ref", "libnttref_scalar.so")
 
 _u64 = C.c_uint64
 _ptr = C.c_void_p
@@ -122,5 +123,35 @@ class Reference:
         return out
 
 
+class ReferenceScalar:
+    """The reference's portable scalar kernel - IterativeNTT over RadixEightScalarLayer<PAdic64Scalar>
+    (layer/scalar/radix-eight.hpp), compiled from /root/reference by oracle/refscalar.cpp.  Correct only below 2^62,
+    hence fixed to the 62-bit test prime; outputs are lazily reduced (compare % N).  CPU baselines B2 (1 thread) and
+    B3 (OpenMP over a batch) of BASELINE.md section 3."""
+    SIZES = (12, 20, 24)
+
+    def __init__(self):
+        if not os.path.exists(REF_SCALAR_SO):
+            raise FileNotFoundError(REF_SCALAR_SO)
+        L = self.lib = C.CDLL(REF_SCALAR_SO)
+        L.refscalar_modulus.restype = _u64
+        L.refscalar_generator.restype = _u64
+        L.refscalar_run.restype = C.c_int
+        L.refscalar_run.argtypes = [C.c_int, C.c_int, _ptr, _ptr, _u64, C.c_int]
+        self.N, self.g = int(L.refscalar_modulus()), int(L.refscalar_generator())
+
+    def run(self, log2_m, inverse, a, batch=1, threads=1, out=None):
+        assert a.size == batch << log2_m
+        out = np.empty_like(a) if out is None else out
+        rc = self.lib.refscalar_run(log2_m, 1 if inverse else 0, _p(out), _p(a), batch, threads)
+        if rc != 0:
+            raise ValueError(f"refscalar_run: unsupported size 2^{log2_m}")
+        return out
+
+
 def have_reference():
     return os.path.exists(REF_SO)
+
+
+def have_reference_scalar():
+    return os.path.exists(REF_SCALAR_SO)

@@ -52,13 +52,14 @@ def test_explicit_splits(emu, oracle, L, splits):
 
 
 @pytest.mark.parametrize("L,splits", [(14, None), (17, [8, 9]), (16, [5, 5, 6]), (13, [1, 12])])
-def test_compact_twiddle_tables(emu, oracle, L, splits, monkeypatch):
+def test_compact_twiddle_tables(emu, oracle, L, splits):
     """The six-step twiddles exist in two forms (whole matrix / two sqrt(M) tables, XNTT_COMPACT_TABLES): the
-    default plans above run the first, these the second - by flag and by a zero table budget."""
+    default plans above run the first, these the second - by flag and by a table budget (xntt_desc::twist_table_max_mb)
+    that holds one direction's matrix but not both (L = 17: 2 MiB each) or neither."""
     assert len(roundtrip(emu, oracle, L, splits=splits, compact_tables=True)) >= 2
     roundtrip(emu, oracle, L, splits=splits, compact_tables=True, inverse_factor=777)
-    monkeypatch.setenv("XNTT_TWIST_TABLE_MAX_MB", "0")
-    roundtrip(emu, oracle, L, splits=splits)
+    roundtrip(emu, oracle, L, splits=splits, twist_table_max_mb=1)
+    roundtrip(emu, oracle, L, splits=splits, twist_table_max_mb=3)
 
 
 @pytest.mark.parametrize("L,batch", [(3, 1), (3, 33), (6, 5), (10, 7), (12, 3), (13, 2), (15, 3)])
@@ -319,7 +320,13 @@ def test_sharded_tiled_variants(emu, oracle, L, splits, G, K):
         assert np.array_equal(got, blocks[r]), (L, splits, G, K, r)
 
 
-@pytest.mark.parametrize("L,splits,G", [(14, [7, 7], 2), (16, [6, 5, 5], 4), (18, [7, 11], 8), (17, [8, 4, 5], 2)])
+@pytest.mark.parametrize("L,splits,G", [
+    (14, [7, 7], 2), (16, [6, 5, 5], 4), (18, [7, 11], 8), (17, [8, 4, 5], 2),
+    # n0 == G: every output row of the column pass belongs to another rank (peer_bits == 0)
+    (15, [3, 12], 8), (13, [1, 12], 2), (14, [2, 6, 6], 4),
+    # inverse: one inner run of pass 1 per peer (block == n1b)
+    (14, [4, 2, 8], 4), (16, [4, 4, 8], 4),
+])
 def test_sharded_peer_store_variants(emu, oracle, L, splits, G):
     """Fused exchange: the pass next to the all-to-all stores straight into every rank's buffer
     (peer pointers).  All ranks live in this process, so 'peer memory' is just the other arrays."""

@@ -132,3 +132,26 @@ def test_dft_point_matches_forward(oracle):
     f = oracle.ntt_forward(a, P0, G0)
     for pos in [0, 1, 2, 511, 512, 1023]:
         assert oracle.dft_point(a, P0, G0, pos) == int(f[pos])
+
+
+def test_reference_scalar_kernel_matches_oracle(oracle):
+    """CPU baseline B2/B3: the reference's scalar IterativeNTT<RadixEightScalarLayer...>
+    compiled from /root/reference (oracle/refscalar.cpp) computes what NTTReference computes at the 62-bit test
+    prime, the check of tests/bench-ntt.cpp:60-64 (`dst[i] % N == dst_ref[i]`); threads only split the batch."""
+    import oracle_lib
+    if not oracle_lib.have_reference_scalar():
+        pytest.skip("oracle/_ref/libnttref_scalar.so not built (needs /root/reference)")
+    ref = oracle_lib.ReferenceScalar()
+    N, g = ref.N, ref.g
+    assert (N, g) == (0x3A00000000000001, 3)
+    for L, batch, threads in [(12, 1, 1), (12, 5, 3), (20, 1, 1), (20, 3, 2)]:
+        m = 1 << L
+        a = oracle.fill_xorshift(m * batch, SEED + L, N)
+        f = ref.run(L, False, a, batch, threads)
+        back = ref.run(L, True, f, batch, threads)
+        for b in range(batch):
+            want = oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), N, g)
+            assert np.array_equal(f[b * m:(b + 1) * m] % np.uint64(N), want), (L, b)
+        assert np.array_equal(back % np.uint64(N), a), L
+    with pytest.raises(ValueError):
+        ref.run(13, False, np.zeros(1 << 13, np.uint64))
