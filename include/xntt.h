@@ -154,6 +154,34 @@ int xntt_shard_forward_cols_peer(const xntt_plan* plan, uint64_t* const* peers, 
 int xntt_shard_inverse_rows_peer(const xntt_plan* plan, uint64_t* const* peers, const uint64_t* src, uint64_t* work,
                                  void* stream);
 
+/* One transform over several GPUs of ONE process (C++-hosted; no collective library, no torch): the library owns one
+ * sharded sub-plan, one stream and two alternating exchange buffers per device, enables peer access between the devices
+ * and orders the single exchange of the six-step split with events.  It stands in for the one call the reference makes
+ * for the whole composition, RecursiveNTT<..., (Blocked)GenericSVELayer, inner, true>::compute_forward / compute_inverse
+ * (include/sventt/kernel/recursive.hpp:48-84, 103-140), whose global transposition (layer/sve/generic.hpp:112-161) is the
+ * exchange.  desc is an ordinary transform descriptor (batch <= 1, shard fields unused, production modulus); devices[]
+ * lists n_devices (2, 4 or 8) CUDA ordinals, rank r = devices[r].  The same ordinal may appear more than once: all ranks
+ * then share that GPU (how the sharded kernels are parity-tested on a single-GPU box).
+ *   xntt_mgpu_forward / _inverse : device-resident shards.  Time domain: rank r holds the column block
+ *       A[:, r*n1/G .. (r+1)*n1/G) of the n0 x n1 row-major matrix as [n0][n1/G] (n0 = xntt_mgpu_n0()); frequency domain:
+ *       rank r holds the r-th contiguous 1/G of the bit-reversed output.  forward: src = time, dst = frequency; inverse
+ *       the other way round.  Work is enqueued on the library's per-rank streams (xntt_mgpu_stream()) and is asynchronous;
+ *       xntt_mgpu_synchronize() waits for all ranks.  dst[r] / src[r] live on devices[r].
+ *   xntt_mgpu_forward_host / _inverse_host : the whole transform on host buffers of m words (natural order in,
+ *       bit-reversed out, and back), scattered to / gathered from the GPUs; returns when dst is complete. */
+typedef struct xntt_mgpu xntt_mgpu;
+int xntt_mgpu_create(xntt_mgpu** mgpu, const xntt_desc* desc, const int32_t* devices, uint32_t n_devices);
+int xntt_mgpu_destroy(xntt_mgpu* mgpu);
+uint32_t xntt_mgpu_devices(const xntt_mgpu* mgpu);
+uint64_t xntt_mgpu_m(const xntt_mgpu* mgpu);
+uint64_t xntt_mgpu_n0(const xntt_mgpu* mgpu);
+void* xntt_mgpu_stream(const xntt_mgpu* mgpu, uint32_t rank);
+int xntt_mgpu_forward(xntt_mgpu* mgpu, uint64_t* const* dst, const uint64_t* const* src);
+int xntt_mgpu_inverse(xntt_mgpu* mgpu, uint64_t* const* dst, const uint64_t* const* src);
+int xntt_mgpu_synchronize(xntt_mgpu* mgpu);
+int xntt_mgpu_forward_host(xntt_mgpu* mgpu, uint64_t* dst, const uint64_t* src);
+int xntt_mgpu_inverse_host(xntt_mgpu* mgpu, uint64_t* dst, const uint64_t* src);
+
 /* PAdic64 element-wise helpers on device buffers (count words each):
  *   to_montgomery      : dst[i] = src[i] * 2^64 mod p     (modmul/sve/p-adic-64.hpp:19-22)
  *   from_montgomery    : dst[i] = src[i] * 2^-64 mod p    (p-adic-64.hpp:24-38, canonical result)

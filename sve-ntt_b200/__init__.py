@@ -71,6 +71,17 @@ SYMBOLS = {
     "xntt_shard_inverse_cols_chunk": (C.c_int, [_P, _U64P, _U64P, C.c_uint32, C.c_uint32, _P]),
     "xntt_shard_forward_cols_peer": (C.c_int, [_P, C.POINTER(C.c_void_p), _U64P, _P]),
     "xntt_shard_inverse_rows_peer": (C.c_int, [_P, C.POINTER(C.c_void_p), _U64P, _U64P, _P]),
+    "xntt_mgpu_create": (C.c_int, [C.POINTER(_P), C.POINTER(Desc), C.POINTER(C.c_int32), C.c_uint32]),
+    "xntt_mgpu_destroy": (C.c_int, [_P]),
+    "xntt_mgpu_devices": (C.c_uint32, [_P]),
+    "xntt_mgpu_m": (C.c_uint64, [_P]),
+    "xntt_mgpu_n0": (C.c_uint64, [_P]),
+    "xntt_mgpu_stream": (C.c_void_p, [_P, C.c_uint32]),
+    "xntt_mgpu_forward": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "xntt_mgpu_inverse": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "xntt_mgpu_synchronize": (C.c_int, [_P]),
+    "xntt_mgpu_forward_host": (C.c_int, [_P, _U64P, _U64P]),
+    "xntt_mgpu_inverse_host": (C.c_int, [_P, _U64P, _U64P]),
     "xntt_to_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
     "xntt_from_montgomery": (C.c_int, [_P, _U64P, _U64P, C.c_size_t, _P]),
     "xntt_multiply_normalize": (C.c_int, [_P, _U64P, _U64P, _U64P, C.c_size_t, _P]),
@@ -126,6 +137,9 @@ class Library:
 
     def plan(self, log2_m, **kw):
         return Plan(self, log2_m, **kw)
+
+    def mgpu(self, log2_m, devices, **kw):
+        return MultiGpu(self, log2_m, devices, **kw)
 
     def transpose(self, dst, src, rows, cols, ld_dst=None, ld_src=None, stream=0):
         self.check(self.lib.xntt_transpose(dst, src, rows, cols, rows if ld_dst is None else ld_dst,
@@ -258,6 +272,64 @@ class Plan:
 
     def multiply_normalize(self, dst, a, b_mont, count, stream=0):
         self._call("xntt_multiply_normalize", dst, a, b_mont, count, stream)
+
+
+class MultiGpu:
+    """xntt_mgpu: one transform over several GPUs of this process (C++-hosted exchange, include/xntt.h)."""
+
+    def __init__(self, library, log2_m, devices, modulus=P0, generator=G0, inverse_factor=None, splits=None,
+                 forward=True, inverse=True):
+        self.L = library
+        d = Desc()
+        d.modulus, d.generator = modulus, generator
+        d.log2_m, d.batch = log2_m, 1
+        d.inverse_factor = (1 << log2_m) if inverse_factor is None else inverse_factor
+        d.flags = (ENABLE_FORWARD if forward else 0) | (ENABLE_INVERSE if inverse else 0)
+        d.device = -1
+        if splits:
+            d.n_splits = len(splits)
+            for i, s in enumerate(splits):
+                d.split_log2[i] = s
+        self.h = C.c_void_p()
+        devs = (C.c_int32 * len(devices))(*devices)
+        library.check(library.lib.xntt_mgpu_create(C.byref(self.h), C.byref(d), devs, len(devices)), "xntt_mgpu_create")
+        self.G = len(devices)
+        self.m = library.lib.xntt_mgpu_m(self.h)
+        self.n0 = library.lib.xntt_mgpu_n0(self.h)
+        self.n1 = self.m // self.n0
+
+    def close(self):
+        if self.h:
+            self.L.lib.xntt_mgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ptrs(self, ptrs):
+        assert len(ptrs) == self.G
+        return (C.c_void_p * self.G)(*ptrs)
+
+    def forward(self, dst_ptrs, src_ptrs):
+        self.L.check(self.L.lib.xntt_mgpu_forward(self.h, self._ptrs(dst_ptrs), self._ptrs(src_ptrs)), "xntt_mgpu_forward")
+
+    def inverse(self, dst_ptrs, src_ptrs):
+        self.L.check(self.L.lib.xntt_mgpu_inverse(self.h, self._ptrs(dst_ptrs), self._ptrs(src_ptrs)), "xntt_mgpu_inverse")
+
+    def synchronize(self):
+        self.L.check(self.L.lib.xntt_mgpu_synchronize(self.h), "xntt_mgpu_synchronize")
+
+    def stream(self, rank):
+        return self.L.lib.xntt_mgpu_stream(self.h, rank) or 0
+
+    def forward_host(self, dst, src):
+        self.L.check(self.L.lib.xntt_mgpu_forward_host(self.h, dst, src), "xntt_mgpu_forward_host")
+
+    def inverse_host(self, dst, src):
+        self.L.check(self.L.lib.xntt_mgpu_inverse_host(self.h, dst, src), "xntt_mgpu_inverse_host")
 
 
 _default = None

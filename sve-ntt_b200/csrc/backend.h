@@ -19,6 +19,11 @@ int host_malloc_pinned(void** p, size_t bytes);
 int host_free_pinned(void* p);
 int memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
 int memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+// strided copies (column blocks of a row-major host matrix <-> compact device blocks); pitches and width in bytes
+int memcpy2d_h2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream);
+int memcpy2d_d2h(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream);
+// let kernels running on `dev` store into memory of `peer` (idempotent)
+int enable_peer_access(int dev, int peer);
 int stream_sync(void* stream);
 // streams and events for the chunk pipeline behind the host entry points of batched plans
 int stream_create(void** stream);

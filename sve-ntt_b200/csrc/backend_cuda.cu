@@ -189,6 +189,34 @@ int memcpy_d2h(void* dst, const void* src, size_t bytes, void* st) {
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)st));
   return 0;
 }
+int memcpy2d_h2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* st) {
+  CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, (cudaStream_t)st));
+  return 0;
+}
+int memcpy2d_d2h(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* st) {
+  CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, (cudaStream_t)st));
+  return 0;
+}
+int enable_peer_access(int dev, int peer) {
+  if (dev == peer) return 0;
+  int can = 0;
+  CU(cudaDeviceCanAccessPeer(&can, dev, peer));
+  if (!can) {
+    g_err = "no peer access between devices " + std::to_string(dev) + " and " + std::to_string(peer);
+    return 1;
+  }
+  int prev = 0;
+  CU(cudaGetDevice(&prev));
+  CU(cudaSetDevice(dev));
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    e = cudaSuccess;
+  }
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) return fail(e);
+  return 0;
+}
 int stream_sync(void* st) {
   CU(cudaStreamSynchronize((cudaStream_t)st));
   return 0;

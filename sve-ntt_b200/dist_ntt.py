@@ -25,8 +25,22 @@ own stream) runs while chunk c+1 computes, and the row half reads the received t
 torch.distributed is plumbing here (NCCL all_to_all_single over NVLink on the box, gloo in the CPU
 tests); the compute is libxntt's xntt_shard_* entry points.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
+
+
+def _stream_scope(stream):
+    """The exchange (symmetric-memory barrier, NCCL all-to-all, tensor copies) runs on torch's CURRENT stream, the
+    kernels on the raw handle the caller passes: make the two the same stream.  0 / None = torch's current stream;
+    any other handle becomes the current stream for the duration of the call.  Returns (context, raw handle)."""
+    if not torch.cuda.is_available():
+        return contextlib.nullcontext(), 0
+    cur = torch.cuda.current_stream()
+    if not stream or stream == cur.cuda_stream:
+        return contextlib.nullcontext(), cur.cuda_stream
+    return torch.cuda.stream(torch.cuda.ExternalStream(stream)), stream
 
 
 class ShardedNTT:
@@ -95,6 +109,11 @@ class ShardedNTT:
     # ---- pipelined path --------------------------------------------------------------------------
     def forward(self, dst, src, stream=0):
         """src: this rank's column block [n0][n1/G]; dst: this rank's row block [n0/G][n1]."""
+        scope, stream = _stream_scope(stream)
+        with scope:
+            return self._forward(dst, src, stream)
+
+    def _forward(self, dst, src, stream):
         if self.mode == "simple":
             return self._forward_simple(dst, src, stream)
         if self.mode == "peer":
@@ -116,6 +135,11 @@ class ShardedNTT:
 
     def inverse(self, dst, src, stream=0):
         """src: row block [n0/G][n1] (bit-reversed order); dst: column block [n0][n1/G]."""
+        scope, stream = _stream_scope(stream)
+        with scope:
+            return self._inverse(dst, src, stream)
+
+    def _inverse(self, dst, src, stream):
         if self.mode == "simple":
             return self._inverse_simple(dst, src, stream)
         if self.mode == "peer":
@@ -151,6 +175,34 @@ class ShardedNTT:
         send.view(G, n0 // G, n1 // G).copy_(recv.view(n0 // G, G, n1 // G).permute(1, 0, 2))
         dist.all_to_all_single(recv, send, group=self.group)
         self.plan.shard_inverse_cols(dst.data_ptr(), recv.data_ptr(), stream)
+
+    # ---- host buffers: what a caller without device-resident data runs (bench.py's e2e figure) --------------
+    def forward_host(self, dst_host, src_host, stream=0):
+        """src_host: this rank's column block in (pinned) host memory; dst_host: its slice of the spectrum.  H2D copy,
+        sharded forward, D2H copy, synchronise."""
+        dev_src, dev_dst = self._host_staging(src_host)
+        scope, stream = _stream_scope(stream)
+        with scope:
+            dev_src.copy_(src_host, non_blocking=True)
+            self._forward(dev_dst, dev_src, stream)
+            dst_host.copy_(dev_dst, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def inverse_host(self, dst_host, src_host, stream=0):
+        dev_src, dev_dst = self._host_staging(src_host)
+        scope, stream = _stream_scope(stream)
+        with scope:
+            dev_src.copy_(src_host, non_blocking=True)
+            self._inverse(dev_dst, dev_src, stream)
+            dst_host.copy_(dev_dst, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def _host_staging(self, like):
+        if getattr(self, "_hstage", None) is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._hstage = (torch.empty(self.local_words, dtype=like.dtype, device=dev),
+                            torch.empty(self.local_words, dtype=like.dtype, device=dev))
+        return self._hstage
 
     def close(self):
         self.plan.close()

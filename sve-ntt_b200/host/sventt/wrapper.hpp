@@ -14,6 +14,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "kernel.hpp"
@@ -41,6 +42,16 @@ inline void check(int status, const char* what) {
 }
 }  // namespace detail
 
+// Devices a subsequently constructed NTT<> spreads ONE transform over (empty or one entry: single GPU).  This is the
+// multi-GPU counterpart of the reference's OpenMP thread team (kernel/recursive.hpp:65): user code stays
+// `sventt::NTT<kernel> ntt; ntt.compute_forward(a.data());`, the library shards the six-step composition
+// (xntt_mgpu_*, one process, peer-to-peer stores, no collective library).  2, 4 or 8 devices; production modulus.
+inline std::vector<int>& default_devices() {
+  static std::vector<int> devices;
+  return devices;
+}
+inline void set_default_devices(std::vector<int> devices) { default_devices() = std::move(devices); }
+
 template <class kernel_type_>
 class NTT {
  public:
@@ -48,6 +59,12 @@ class NTT {
   using modulus_type = typename kernel_type::modulus_type;
 
   explicit NTT(bool enable_forward = true, bool enable_inverse = true, bool /*allocate_huge_pages*/ = true,
+               std::uint32_t batch = 1, int device = -1)
+      : NTT(batch == 1 && device < 0 ? default_devices() : std::vector<int>{}, enable_forward, enable_inverse, batch,
+            device) {}
+
+  // one transform over several GPUs of this process (see set_default_devices)
+  explicit NTT(const std::vector<int>& devices, bool enable_forward = true, bool enable_inverse = true,
                std::uint32_t batch = 1, int device = -1) {
     xntt_desc d{};
     d.modulus = modulus_type::get_modulus();
@@ -61,23 +78,35 @@ class NTT {
     d.device = device;
     std::vector<std::uint32_t> splits;
     kernel_type::append_splits(splits);
+    const bool multi = devices.size() > 1;
+    std::vector<std::int32_t> devs(devices.begin(), devices.end());
+    auto create = [&]() {
+      return multi ? xntt_mgpu_create(&mgpu_, &d, devs.data(), static_cast<std::uint32_t>(devs.size()))
+                   : xntt_plan_create(&plan_, &d);
+    };
+    if (!multi && devices.size() == 1) d.device = devices[0];
     int status = XNTT_ERR_UNSUPPORTED;
     if (splits.size() >= 2 && splits.size() <= XNTT_MAX_SPLITS) {
       d.n_splits = static_cast<std::uint32_t>(splits.size());
       for (std::size_t i = 0; i < splits.size(); ++i) d.split_log2[i] = splits[i];
-      status = xntt_plan_create(&plan_, &d);
+      status = create();
     }
-    if (status == XNTT_ERR_UNSUPPORTED) {
+    if (status == XNTT_ERR_UNSUPPORTED || (multi && status == XNTT_ERR_INVALID && d.n_splits != 0)) {
       // the composition asks for a tile shape the shared-memory kernels do not have (or is a single
-      // unit): same transform, planner's own decomposition
+      // unit, or a first split the device count does not divide): same transform, planner's own decomposition
       d.n_splits = 0;
-      status = xntt_plan_create(&plan_, &d);
+      status = create();
     }
     detail::check(status, "sventt::NTT");
   }
   NTT(const NTT&) = delete;
   NTT& operator=(const NTT&) = delete;
-  ~NTT() { xntt_plan_destroy(plan_); }
+  ~NTT() {
+    xntt_plan_destroy(plan_);
+    xntt_mgpu_destroy(mgpu_);
+  }
+  // number of GPUs this transform runs on
+  std::uint32_t get_device_count() const { return mgpu_ ? xntt_mgpu_devices(mgpu_) : 1u; }
 
   static constexpr std::uint64_t get_m() { return kernel_type::get_m(); }
 
@@ -100,9 +129,29 @@ class NTT {
     detail::check(xntt_forward_multiply(plan_, dst, src, b_mont, stream), "compute_forward_multiply");
   }
   const xntt_plan* plan() const { return plan_; }
+  xntt_mgpu* mgpu() const { return mgpu_; }
+  // multi-GPU plans, device-resident shards (layouts: include/xntt.h, xntt_mgpu_forward); asynchronous
+  void compute_forward_shards(std::uint64_t* const* dst, const std::uint64_t* const* src) const {
+    detail::check(mgpu_ ? xntt_mgpu_forward(mgpu_, dst, src) : XNTT_ERR_STATE, "compute_forward_shards");
+  }
+  void compute_inverse_shards(std::uint64_t* const* dst, const std::uint64_t* const* src) const {
+    detail::check(mgpu_ ? xntt_mgpu_inverse(mgpu_, dst, src) : XNTT_ERR_STATE, "compute_inverse_shards");
+  }
+  void synchronize() const {
+    detail::check(mgpu_ ? xntt_mgpu_synchronize(mgpu_) : xntt_stream_synchronize(nullptr), "synchronize");
+  }
 
  private:
   void run(std::uint64_t* dst, const std::uint64_t* src, bool inverse) const {
+    if (mgpu_) {
+      // whole transform on host buffers, scattered over the GPUs (device-resident data: compute_*_shards)
+      const int kd = xntt_pointer_is_device(dst), ks = xntt_pointer_is_device(src);
+      int status = (kd == 0 && ks == 0)
+                       ? (inverse ? xntt_mgpu_inverse_host(mgpu_, dst, src) : xntt_mgpu_forward_host(mgpu_, dst, src))
+                       : XNTT_ERR_INVALID;
+      detail::check(status, inverse ? "compute_inverse" : "compute_forward");
+      return;
+    }
     const int kd = xntt_pointer_is_device(dst), ks = xntt_pointer_is_device(src);
     if (kd < 0 || ks < 0) detail::throw_status(kd < 0 ? kd : ks, "compute");
     int status;
@@ -118,6 +167,7 @@ class NTT {
   }
 
   xntt_plan* plan_ = nullptr;
+  xntt_mgpu* mgpu_ = nullptr;
 };
 
 }  // namespace sventt

@@ -150,6 +150,30 @@ using kernel_type = RecursiveNTT<modulus_type, n, BlockedGenericSVELayer<modmul_
                                  inner<n1, n>, true>;
 }  // namespace big24
 
+// ---- one transform over several GPUs: production modulus, six-step compositions (2^10 x 2^10 and the README shape)
+namespace mg20 {
+using modulus_type = prod::modulus_type;
+using modmul_type = prod::modmul_type;
+constexpr std::uint64_t n = one << 20, n0 = one << 10, n1 = one << 10;
+template <std::uint64_t len, std::uint64_t f>
+using inner = IterativeNTT<modulus_type, len, RadixTwoSVELayer<modmul_type, len, len>,
+                           RadixEightSVELayer<modmul_type, len, (len >> 1)>, RadixEightSVELayer<modmul_type, len, (len >> 4)>,
+                           RadixEightSVELayer<modmul_type, len, (len >> 7), f>>;
+using kernel_type = RecursiveNTT<modulus_type, n, BlockedGenericSVELayer<modmul_type, n, inner<n0, 1>, 32, 2, 128>,
+                                 inner<n1, n>, true>;
+}  // namespace mg20
+namespace mg17 {
+using modulus_type = prod::modulus_type;
+using modmul_type = prod::modmul_type;
+constexpr std::uint64_t n = one << 17, n0 = one << 8, n1 = one << 9;
+using ntt0_type = IterativeNTT<modulus_type, n0, RadixEightSVELayer<modmul_type, n0, n0>,
+                               RadixEightSVELayer<modmul_type, n0, (n0 >> 3)>, RadixFourSVELayer<modmul_type, n0, (n0 >> 6)>>;
+using ntt1_type = IterativeNTT<modulus_type, n1, RadixEightSVELayer<modmul_type, n1, n1>,
+                               RadixEightSVELayer<modmul_type, n1, (n1 >> 3)>, RadixEightSVELayer<modmul_type, n1, (n1 >> 6), n>>;
+using kernel_type =
+    RecursiveNTT<modulus_type, n, BlockedGenericSVELayer<modmul_type, n, ntt0_type, 32, 2, 128>, ntt1_type, true>;
+}  // namespace mg17
+
 static int failures = 0;
 
 // bench-ntt.cpp:20-65 without the Google Benchmark loop
@@ -222,6 +246,26 @@ int main(int argc, char** argv) {
     both<rec_four13::kernel_type>("recursive, scalar, four-step");
     both<readme::kernel_type>("README blocked six-step 2^8 x 2^9");
     if (big) both<big24::kernel_type>("blocked six-step 2^12 x 2^12");
+    // the same user code, one transform spread over several GPUs by the library (xntt_mgpu_*): by default every
+    // rank on device 0, `--devices 0,1,2,3` names real ones
+    {
+      std::vector<int> devs{0, 0, 0, 0};
+      for (int i = 1; i + 1 < argc; ++i)
+        if (std::string{argv[i]} == "--devices") {
+          devs.clear();
+          for (const char* p = argv[i + 1]; *p; ++p)
+            if (*p >= '0' && *p <= '9') devs.push_back(*p - '0');
+        }
+      set_default_devices(devs);
+      both<mg20::kernel_type>("multi-GPU six-step 2^10 x 2^10, G=" + std::to_string(devs.size()));
+      set_default_devices(std::vector<int>(devs.begin(), devs.begin() + 2));
+      both<mg17::kernel_type>("multi-GPU README shape 2^8 x 2^9, G=2");
+      if (big) {
+        set_default_devices(devs);
+        both<big24::kernel_type>("multi-GPU six-step 2^12 x 2^12, G=" + std::to_string(devs.size()));
+      }
+      set_default_devices({});
+    }
     // Modulus / PAdic64 scalar identities used by the examples
     using modulus_type = prod::modulus_type;
     using P = PAdic64<modulus_type>;

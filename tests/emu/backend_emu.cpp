@@ -181,6 +181,14 @@ int memcpy_d2h(void* dst, const void* src, size_t bytes, void*) {
   memmove(dst, src, bytes);
   return 0;
 }
+int memcpy2d_h2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void*) {
+  for (size_t r = 0; r < height; ++r) memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+  return 0;
+}
+int memcpy2d_d2h(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* st) {
+  return memcpy2d_h2d(dst, dpitch, src, spitch, width, height, st);
+}
+int enable_peer_access(int, int) { return 0; }
 int stream_sync(void*) { return 0; }
 // the emulator executes every "launch" and copy at once, in program order: streams and events are tokens
 int stream_create(void** st) {

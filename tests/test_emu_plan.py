@@ -398,3 +398,49 @@ def test_host_entry_point_pipelines(emu, oracle, L, batch, splits):
     # in place
     plan.forward_host(a.ctypes.data, a.ctypes.data)
     assert np.array_equal(a, out)
+
+
+@pytest.mark.parametrize("L,splits,G", [(14, None, 2), (16, [6, 5, 5], 4), (18, [7, 11], 8), (15, [3, 12], 8),
+                                        (17, [8, 4, 5], 2)])
+def test_mgpu_plan_in_one_process(emu, oracle, L, splits, G):
+    """xntt_mgpu_*: the C++-hosted multi-GPU plan (csrc/mgpu.cpp) - G sharded sub-plans, peer-store exchange, event
+    ordering - against the oracle, through the device-shard entry points and the whole-transform host entry points;
+    three transforms in a row so that both exchange buffers get reused.  (The emulator has one 'device'; on a GPU
+    box the same test runs with every rank on device 0, tests/test_gpu_parity.py.)"""
+    m = 1 << L
+    mg = emu.mgpu(L, list(range(G)), splits=splits, inverse_factor=m)
+    n0, n1 = mg.n0, mg.n1
+    assert n0 * n1 == m
+    for rep in range(3):
+        a = oracle.fill_xorshift(m, SEED + 40 + rep, P0)
+        want = oracle.ntt_forward(a, P0, G0)
+        A = a.reshape(n0, n1)
+        blocks = [np.ascontiguousarray(A[:, r * n1 // G:(r + 1) * n1 // G]).reshape(-1) for r in range(G)]
+        outs = [np.full(m // G, 0xDEAD, np.uint64) for _ in range(G)]
+        mg.forward([o.ctypes.data for o in outs], [b.ctypes.data for b in blocks])
+        mg.synchronize()
+        assert np.array_equal(np.concatenate(outs), want), (L, splits, G, rep)
+        backs = [np.full(m // G, 0xBEEF, np.uint64) for _ in range(G)]
+        mg.inverse([b.ctypes.data for b in backs], [o.ctypes.data for o in outs])
+        mg.synchronize()
+        for r in range(G):
+            assert np.array_equal(backs[r], blocks[r]), (L, splits, G, rep, r)
+        # whole transform on host buffers
+        got = np.empty_like(a)
+        mg.forward_host(got.ctypes.data, a.ctypes.data)
+        assert np.array_equal(got, want)
+        back = np.empty_like(a)
+        mg.inverse_host(back.ctypes.data, got.ctypes.data)
+        assert np.array_equal(back, a)
+    mg.close()
+
+
+def test_mgpu_argument_checks(emu):
+    import pytest as _pt
+    for devs in ([0], [0, 1, 2], list(range(16))):
+        with _pt.raises(Exception):
+            emu.mgpu(16, devs)
+    with _pt.raises(Exception):
+        emu.mgpu(16, [0, 1], modulus=0xFFFFFFFF00000001, generator=7)  # address-mapped kernels: production prime only
+    with _pt.raises(Exception):
+        emu.mgpu(12, [0, 1])  # single-pass size: nothing to exchange

@@ -288,25 +288,168 @@ def test_batched_256x2p20(cuda_lib, oracle):
     plan.close()
 
 
-@pytest.mark.parametrize("L", [26, 28])
+def test_three_pass_full_compare_2p26(cuda_lib, oracle):
+    """Three-pass plan (the shape every 2^30 shard takes), every output word against the oracle at 2^26
+    (the oracle needs ~25 s for it), forward and inverse - the contract of tests/bench-ntt.cpp:60-64."""
+    import torch
+    L = 26
+    m = 1 << L
+    plan = cuda_lib.plan(L)
+    assert len(plan.splits) == 3
+    a = oracle.fill_xorshift(m, SEED + L, P0)
+    src = dev(a)
+    dst = torch.empty_like(src)
+    plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+    want = oracle.ntt_forward(a, P0, G0)
+    got = host(dst)
+    assert np.array_equal(got, want)
+    plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
+    assert torch.equal(dst, src)
+    plan.close()
+
+
+@pytest.mark.parametrize("L", [28, 30])
 def test_three_pass_sizes(cuda_lib, oracle, L):
-    """Sizes whose shards BASELINE configs[3] hands to one GPU: round trip and direct spot words."""
+    """BASELINE configs[3] sizes on one GPU: directly evaluated output words (oracle.dft_point on a sparse input - a
+    dense 2^30-term sum per word is minutes of CPU), linearity against a dense input, and the round trip."""
     import torch
     m = 1 << L
     plan = cuda_lib.plan(L)
     assert len(plan.splits) == 3
+    # sparse input: 64 non-zero words at scattered positions -> every output word is a 64-term sum the oracle
+    # evaluates exactly; checks 4096 output positions spread over all tiles of all three passes
+    rng = np.random.default_rng(L)
+    pos = np.unique(rng.integers(0, m, 64, dtype=np.int64))
+    val = rng.integers(1, P0, pos.size, dtype=np.uint64)
+    sparse = torch.zeros(m, dtype=torch.int64, device="cuda")
+    sparse[torch.from_numpy(pos).cuda()] = torch.from_numpy(val.view(np.int64)).cuda()
+    out = torch.empty_like(sparse)
+    plan.forward(out.data_ptr(), sparse.data_ptr(), stream())
+    omega = oracle.root_forward(P0, G0, m)
+    idx = np.unique(np.concatenate([rng.integers(0, m, 4000, dtype=np.int64), [0, 1, m // 2, m - 1, m - 2]]))
+    got = host(out[torch.from_numpy(idx).cuda()])
+    for i, g in zip(idx, got):
+        k = int(f"{int(i):0{L}b}"[::-1], 2)  # output index i holds frequency bitrev(i)
+        want = 0
+        for p_, v_ in zip(pos, val):
+            want = (want + int(v_) * pow(omega, (k * int(p_)) % m, P0)) % P0
+        assert int(g) == want, (L, int(i))
+    # linearity: F(dense + sparse) == F(dense) + F(sparse), all words
     gen = torch.Generator(device="cuda")
     gen.manual_seed(L)
-    src = torch.randint(0, 2**62, (m,), dtype=torch.int64, device="cuda", generator=gen)
-    dst = torch.empty_like(src)
-    plan.forward(dst.data_ptr(), src.data_ptr(), stream())
-    if L <= 26:
-        a = host(src)
-        for pos in (0, 3, m // 2 + 1, m - 1):
-            assert int(dst[pos].item()) & (2**64 - 1) == oracle.dft_point(a, P0, G0, pos)
-    plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
-    assert torch.equal(dst, src)
+    dense = torch.randint(0, 2**62, (m,), dtype=torch.int64, device="cuda", generator=gen)
+    fd = torch.empty_like(dense)
+    plan.forward(fd.data_ptr(), dense.data_ptr(), stream())
+    # (dense + sparse) mod p: only the 64 sparse positions change
+    summed = dense.clone()
+    sel = torch.from_numpy(pos).cuda()
+    sv = host(sparse[sel]).astype(object) + host(dense[sel]).astype(object)
+    summed[sel] = torch.from_numpy(np.array([int(x) % P0 for x in sv], dtype=np.uint64).view(np.int64)).cuda()
+    del sparse
+    fs = torch.empty_like(dense)
+    plan.forward(fs.data_ptr(), summed.data_ptr(), stream())
+    del summed
+    # fs - fd must equal out (mod p): a random sample of positions plus the directly evaluated ones
+    samp = torch.from_numpy(np.unique(np.concatenate([rng.integers(0, m, 20000, dtype=np.int64), idx]))).cuda()
+    a_, b_, c_ = (host(x[samp]).astype(object) for x in (fs, fd, out))
+    assert all((int(x) - int(y)) % P0 == int(z) for x, y, z in zip(a_, b_, c_))
+    del fs, out
+    plan.inverse(fd.data_ptr(), fd.data_ptr(), stream())
+    assert torch.equal(fd, dense)
     plan.close()
+
+
+@pytest.mark.parametrize("L,G,splits", [(20, 2, None), (20, 4, [10, 10]), (20, 8, None), (24, 2, None), (24, 4, None),
+                                        (24, 8, None), (21, 4, [7, 7, 7]), (15, 8, [3, 12]), (26, 8, None)])
+def test_sharded_plan_on_one_gpu(cuda_lib, oracle, L, G, splits):
+    """The N > 1 path on a single-GPU box: the C++-hosted multi-GPU plan (xntt_mgpu_*) with every rank on device 0.
+    The peer-store kernels only need addresses, so 'peer memory' is simply the other ranks' buffers; every rank's
+    slice is compared with the oracle word for word, forward and inverse, twice (both exchange buffers)."""
+    import torch
+    m = 1 << L
+    mg = cuda_lib.mgpu(L, [0] * G, splits=splits)
+    n0, n1 = mg.n0, mg.n1
+    for rep in range(2):
+        a = oracle.fill_xorshift(m, SEED + 100 * rep + L, P0)
+        want = oracle.ntt_forward(a, P0, G0) if L <= 24 else None
+        full = dev(a)
+        blocks = [full.view(n0, n1)[:, r * n1 // G:(r + 1) * n1 // G].contiguous().view(-1) for r in range(G)]
+        outs = [torch.full((m // G,), 0x5555555555555555, dtype=torch.int64, device="cuda") for _ in range(G)]
+        torch.cuda.synchronize()
+        mg.forward([o.data_ptr() for o in outs], [b.data_ptr() for b in blocks])
+        mg.synchronize()
+        got = host(torch.cat(outs))
+        if want is not None:
+            assert np.array_equal(got, want), (L, G, rep)
+        else:
+            # 2^26: against the single-GPU plan (itself compared with the oracle in test_three_pass_full_compare_2p26)
+            ref = cuda_lib.plan(L)
+            w = torch.empty_like(full)
+            ref.forward(w.data_ptr(), full.data_ptr(), stream())
+            torch.cuda.synchronize()
+            assert np.array_equal(got, host(w)), (L, G, rep)
+            ref.close()
+        backs = [torch.empty_like(b) for b in blocks]
+        mg.inverse([b.data_ptr() for b in backs], [o.data_ptr() for o in outs])
+        mg.synchronize()
+        for r in range(G):
+            assert torch.equal(backs[r], blocks[r]), (L, G, rep, r)
+    # whole transform through the host entry points (strided scatter / gather of the column blocks)
+    if L <= 24:
+        out = np.empty_like(a)
+        mg.forward_host(out.ctypes.data, a.ctypes.data)
+        assert np.array_equal(out, want)
+        back = np.empty_like(a)
+        mg.inverse_host(back.ctypes.data, out.ctypes.data)
+        assert np.array_equal(back, a)
+    mg.close()
+
+
+@pytest.mark.parametrize("L,G,K,splits", [(20, 2, 4, None), (22, 4, 2, None), (21, 8, 1, [7, 7, 7]), (24, 8, 4, None)])
+def test_sharded_chunked_exchange_on_one_gpu(cuda_lib, oracle, L, G, K, splits):
+    """The NCCL-pipelined variant's kernels (column pass per chunk into message layout, tiled row half) with all ranks
+    on device 0 and the all-to-all played by tensor copies: same check as above."""
+    import torch
+    m = 1 << L
+    plans = [cuda_lib.plan(L, splits=splits, shard_count=G, shard_rank=r) for r in range(G)]
+    n0 = 1 << plans[0].splits[0]
+    n1 = m // n0
+    w = n1 // (G * K)
+    msg = (n0 // G) * w
+    a = oracle.fill_xorshift(m, SEED + L + G, P0)
+    want = oracle.ntt_forward(a, P0, G0)
+    full = dev(a)
+    st = stream()
+    blocks = [full.view(n0, n1)[:, r * n1 // G:(r + 1) * n1 // G].contiguous().view(-1) for r in range(G)]
+    send = [torch.empty(m // G, dtype=torch.int64, device="cuda") for _ in range(G)]
+    for r in range(G):
+        for c in range(K):
+            plans[r].shard_forward_cols_chunk(send[r].data_ptr(), blocks[r].data_ptr(), c, K, st)
+    recv = [torch.empty(m // G, dtype=torch.int64, device="cuda") for _ in range(G)]
+    for r in range(G):
+        for s_ in range(G):
+            recv[s_].view(K, G, msg)[:, r, :] = send[r].view(K, G, msg)[:, s_, :]
+    outs = []
+    for r in range(G):
+        o = torch.empty(m // G, dtype=torch.int64, device="cuda")
+        plans[r].shard_forward_rows_tiled(o.data_ptr(), recv[r].data_ptr(), K, st)
+        outs.append(o)
+    assert np.array_equal(host(torch.cat(outs)), want), (L, G, K)
+    tiles = [torch.empty(m // G, dtype=torch.int64, device="cuda") for _ in range(G)]
+    work = torch.empty(m // G, dtype=torch.int64, device="cuda")
+    for r in range(G):
+        plans[r].shard_inverse_rows_tiled(tiles[r].data_ptr(), outs[r].data_ptr(), work.data_ptr(), K, st)
+    back = [torch.empty(m // G, dtype=torch.int64, device="cuda") for _ in range(G)]
+    for r in range(G):
+        for s_ in range(G):
+            back[s_].view(K, G, msg)[:, r, :] = tiles[r].view(K, G, msg)[:, s_, :]
+    for r in range(G):
+        got = torch.empty(m // G, dtype=torch.int64, device="cuda")
+        for c in range(K):
+            plans[r].shard_inverse_cols_chunk(got.data_ptr(), back[r].data_ptr(), c, K, st)
+        assert torch.equal(got, blocks[r]), (L, G, K, r)
+    for p_ in plans:
+        p_.close()
 
 
 def test_error_paths(cuda_lib, pkg):

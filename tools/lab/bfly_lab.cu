@@ -38,6 +38,10 @@ __device__ __forceinline__ void bfly(u64& x0, u64& x1, u64 w, u64 wp) {
     lab::bf_mixed<1>(x0, x1, w, wp);
   } else if constexpr (V == 11) {
     lab::bf_mixed<3>(x0, x1, w, wp);
+  } else if constexpr (V == 12) {
+    lab::bf_v12(x0, x1, w, wp);
+  } else if constexpr (V == 13) {
+    lab::bf_v13(x0, x1, w, wp);
   }
 }
 
@@ -167,6 +171,10 @@ int main(int argc, char** argv) {
   int rc = 0;
   const int only = argc > 2 ? atoi(argv[2]) : -1;
   if (only < 0 || only == 9) rc |= run<9, 2>("v9_field_cuh_now", iters);
+  if (only < 0 || only == 12) rc |= run<12, 2>("v12_lhi_from_qP", iters);
+  if (only < 0 || only == 13) rc |= run<13, 2>("v13_lhi_from_qP_q1P0_shifts", iters);
+  if (only < 0 || only == 10) rc |= run<10, 2>("v10_fix_alu_sum", iters);
+  if (only < 0 || only == 11) rc |= run<11, 2>("v11_fix_alu_both", iters);
   if (only < 0 || only == 6) rc |= run<6, 2>("v6_probe_nofix", iters, false);
   if (only < 0 || only == 7) rc |= run<7, 2>("v7_probe_mont_only", iters, false);
   return rc;

@@ -217,3 +217,76 @@ __device__ __forceinline__ void bf_mixed(u64& x0, u64& x1, u64 w, u64 wp) {
   x1 = (MODE & 2) ? fix_alu(d, d1) : f.fix(d, d1);
 }
 }
+
+namespace lab {
+// v12: the second word of the low product taken from the q*P side.  The low 64 bits of a*w and q*P coincide, so
+// L.hi = lo32(q0*P1 + q1*P0) + hi32(q0*P0) as well, and with P0 = 2^31 + 1 that last term is shifts and one add
+// instead of the IMAD.WIDE a0*w0:  hi32(q0*(2^31+1)) = (q0 >> 1) + carry(q0 + (q0 << 31)).
+// carry2 is then the plain carry of yl + vh', carry1 = [L.hi < xl] (the roles of v8 swapped).  9 wide + 4 narrow.
+__device__ __forceinline__ void mont_parts_v12(u64 a, u64 w, u64 wp, u64& h1, u64& h2) {
+  u32 a0, a1, w0, w1, q0, q1, h1l, h1h, h2l, h2h;
+  unpack64(a, a0, a1);
+  unpack64(w, w0, w1);
+  unpack64(a * wp, q0, q1);
+  u32 vhp;  // explicit carry chain: written as C, ptxas folds it back into IMAD.HI q0 * 0x80000001
+  asm("{\n\t.reg .u32 s, h;\n\tshl.b32 s, %1, 31;\n\tshr.u32 h, %1, 1;\n\tadd.cc.u32 s, s, %1;\n\taddc.u32 %0, h, 0;\n\t}"
+      : "=r"(vhp) : "r"(q0));
+  asm("{\n\t.reg .u32 xl, xh, xc, lh, yl, yh, yc, t;\n\t"
+      "mul.lo.u32 yl, %8, %11;\n\tmul.hi.u32 yh, %8, %11;\n\t"  // q0*P1
+      "mad.lo.cc.u32 yl, %9, %10, yl;\n\tmadc.hi.cc.u32 yh, %9, %10, yh;\n\taddc.u32 yc, 0, 0;\n\t"  // + q1*P0
+      "add.cc.u32 lh, yl, %12;\n\t"  // L.hi, carry2
+      "madc.lo.cc.u32 %2, %9, %11, yh;\n\tmadc.hi.u32 %3, %9, %11, yc;\n\t"  // h2
+      "mul.lo.u32 xl, %4, %7;\n\tmul.hi.u32 xh, %4, %7;\n\t"  // a0*w1
+      "mad.lo.cc.u32 xl, %5, %6, xl;\n\tmadc.hi.cc.u32 xh, %5, %6, xh;\n\taddc.u32 xc, 0, 0;\n\t"  // + a1*w0
+      "not.b32 t, lh;\n\tadd.cc.u32 t, xl, t;\n\t"  // carry1 = [xl > L.hi]
+      "madc.lo.cc.u32 %0, %5, %7, xh;\n\tmadc.hi.u32 %1, %5, %7, xc;\n\t"  // h1
+      "}"
+      : "=r"(h1l), "=r"(h1h), "=r"(h2l), "=r"(h2h)
+      : "r"(a0), "r"(a1), "r"(w0), "r"(w1), "r"(q0), "r"(q1), "r"(P_LO), "r"(P_HI), "r"(vhp));
+  h1 = pack64(h1l, h1h);
+  h2 = pack64(h2l, h2h);
+}
+__device__ __forceinline__ void bf_v12(u64& x0, u64& x1, u64 w, u64 wp) {
+  const xntt::F0 f{};
+  u64 h1, h2, u, s, d;
+  u32 m, d0, d1;
+  mont_parts_v12(x1, w, wp, h1, h2);
+  xntt::sub_borrow_mask(h1, h2, u, m);
+  xntt::add_carry_plus(x0, u, m, s, d0);
+  xntt::sub_borrow_minus(x0, u, m, d, d1);
+  x0 = f.fix(s, d0);
+  x1 = f.fix(d, d1);
+}
+// v13: v12 with q1*P0 = q1 + (q1 << 31) by shifts as well (8 wide): y = q0*P1 + q1*P0 as a 65-bit sum
+__device__ __forceinline__ void bf_v13(u64& x0, u64& x1, u64 w, u64 wp) {
+  const xntt::F0 f{};
+  u32 a0, a1, w0, w1, q0, q1, h1l, h1h, h2l, h2h;
+  unpack64(x1, a0, a1);
+  unpack64(w, w0, w1);
+  unpack64(x1 * wp, q0, q1);
+  u32 vhp, zl, zh;
+  asm("{\n\t.reg .u32 s, h;\n\tshl.b32 s, %1, 31;\n\tshr.u32 h, %1, 1;\n\tadd.cc.u32 s, s, %1;\n\taddc.u32 %0, h, 0;\n\t}"
+      : "=r"(vhp) : "r"(q0));
+  // z = q1*P0 = q1 + (q1 << 31) < 2^63 + 2^32
+  asm("{\n\t.reg .u32 s, h;\n\tshl.b32 s, %2, 31;\n\tshr.u32 h, %2, 1;\n\tadd.cc.u32 %0, s, %2;\n\taddc.u32 %1, h, 0;\n\t}"
+      : "=r"(zl), "=r"(zh) : "r"(q1));
+  asm("{\n\t.reg .u32 xl, xh, xc, lh, yl, yh, yc, t;\n\t"
+      "mad.lo.cc.u32 yl, %8, %11, %13;\n\tmadc.hi.cc.u32 yh, %8, %11, %14;\n\taddc.u32 yc, 0, 0;\n\t"  // q0*P1 + z
+      "add.cc.u32 lh, yl, %12;\n\t"
+      "madc.lo.cc.u32 %2, %9, %11, yh;\n\tmadc.hi.u32 %3, %9, %11, yc;\n\t"
+      "mul.lo.u32 xl, %4, %7;\n\tmul.hi.u32 xh, %4, %7;\n\t"
+      "mad.lo.cc.u32 xl, %5, %6, xl;\n\tmadc.hi.cc.u32 xh, %5, %6, xh;\n\taddc.u32 xc, 0, 0;\n\t"
+      "not.b32 t, lh;\n\tadd.cc.u32 t, xl, t;\n\t"
+      "madc.lo.cc.u32 %0, %5, %7, xh;\n\tmadc.hi.u32 %1, %5, %7, xc;\n\t"
+      "}"
+      : "=r"(h1l), "=r"(h1h), "=r"(h2l), "=r"(h2h)
+      : "r"(a0), "r"(a1), "r"(w0), "r"(w1), "r"(q0), "r"(q1), "r"(P_LO), "r"(P_HI), "r"(vhp), "r"(zl), "r"(zh));
+  u64 u, s, d;
+  u32 m, d0, d1;
+  xntt::sub_borrow_mask(pack64(h1l, h1h), pack64(h2l, h2h), u, m);
+  xntt::add_carry_plus(x0, u, m, s, d0);
+  xntt::sub_borrow_minus(x0, u, m, d, d1);
+  x0 = f.fix(s, d0);
+  x1 = f.fix(d, d1);
+}
+}  // namespace lab
