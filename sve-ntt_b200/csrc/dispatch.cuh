@@ -24,8 +24,60 @@ cudaError_t launch_inv_row_rt(int logn, const PassParams& prm, unsigned grid, cu
 cudaError_t launch_fwd_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 
+#if XNTT_TMA_ROWS
+// Measured variant (XNTT_TMA_ROWS): tensor map over the source of a 2^13 row pass viewed as rows of 16 residues
+// (128 bytes, 128-byte swizzle), box = 16 x 256.  The encoder comes from the driver through the runtime
+// (cudaGetDriverEntryPoint), so the library still does not link libcuda.
+inline cudaError_t make_row_tensor_map(CUtensorMap* map, const u64* base, u64 rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    encode = (encode_fn)fn;
+  }
+  const cuuint64_t dims[2] = {16, rows * 512};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {16, 256}, estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <class F, bool INV, int TWIST>
+cudaError_t launch_row_tma(const PassParams& prm, unsigned grid, cudaStream_t st) {
+  auto kern = row_kernel_tma<F, INV, TWIST>;
+  constexpr int kSmem = 65536 + 1024 + 16;  // tile, alignment slack, mbarrier
+  static std::atomic<bool> attr_done_on[64];
+  static std::mutex attr_mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!attr_done_on[dev & 63].load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lock(attr_mu);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return e;
+    attr_done_on[dev & 63].store(true, std::memory_order_release);
+  }
+  CUtensorMap map;
+  e = make_row_tensor_map(&map, prm.src, prm.rows);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, kSmem, st>>>(prm, map);
+  return cudaGetLastError();
+}
+#endif
+
 template <class F, int LOGN, bool COL, bool INV, bool MAP, int TWIST>
 cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st) {
+#if XNTT_TMA_ROWS
+  if constexpr (!COL && !MAP && LOGN == 13 && F::kStatic) return launch_row_tma<F, INV, TWIST>(prm, grid, st);
+#endif
   constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
   auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, TWIST, MAP>;

@@ -27,6 +27,9 @@
 #pragma once
 #if !defined(XNTT_HOST_EMU)
 #include <cuda_runtime.h>
+#if defined(XNTT_TMA_ROWS) && XNTT_TMA_ROWS
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 #endif
 
 #include <cstdint>
@@ -103,10 +106,10 @@ __device__ __forceinline__ int swz(int k) {
   return k ^ ((k >> LOGRN) & Slot<C>::kSwzMask);
 }
 
-template <int LOGN_, int LOGW_, int C_, bool COL_, bool MAP_ = false>
+template <int LOGN_, int LOGW_, int C_, bool COL_, bool MAP_ = false, bool TMA_ = false>
 struct PassCfg {
   static constexpr int LOGN = LOGN_, LOGW = LOGW_, C = C_;
-  static constexpr bool COL = COL_, MAP = MAP_;
+  static constexpr bool COL = COL_, MAP = MAP_, TMA = TMA_;
   static constexpr int N = 1 << LOGN, W = 1 << LOGW;
   static constexpr int NP = W / C;  // column groups per tile
   static constexpr int LOGNP = LOGW - (C == 2 ? 1 : 0);
@@ -214,9 +217,65 @@ __device__ __forceinline__ ulonglong2 ld_stream2(const u64* p) {
 #endif
 }
 
+// XNTT_PROBE_NOMEM (development probe, never a product build): compile the global loads and stores of tile data out -
+// loads become register arithmetic, stores are predicated on a value that never occurs - to see what the memory phases
+// of a pass cost ("Why not TMA"; tools/gpu_variants.py times the variant next to the product).
+#ifndef XNTT_PROBE_NOMEM
+#define XNTT_PROBE_NOMEM 0
+#endif
+// XNTT_TMA_ROWS (measured variant, off in the product build): the 2^13 row pass stages its tile through a bulk tensor
+// copy (cp.async.bulk.tensor.2d + mbarrier, SASS UTMALDG) instead of per-thread LDG, see row_tile_tma_load below.
+#ifndef XNTT_TMA_ROWS
+#define XNTT_TMA_ROWS 0
+#endif
+
+#if XNTT_TMA_ROWS && !defined(XNTT_HOST_EMU)
+// The tile (2^13 contiguous residues = 64 KiB) is described to the TMA unit as 512 rows of 16 residues (128 bytes) with
+// the 128-byte swizzle: 16-byte chunk c of row r lands at chunk c ^ (r & 7).  As a slot index (8-byte slots):
+//   pos_T(k) = k ^ (((k >> 4) & 7) << 1)
+// Both first stages read conflict-free from that layout (forward: a warp reads 32 consecutive k; inverse: every lane
+// reads 8 consecutive k, 16-byte accesses of 8 lanes spread over all 8 chunks) and write the kernel's own swizzle
+// swz(k) = k ^ ((k >> 3) & 15) in place: both permutations stay inside aligned groups of 16 slots, and the tasks that
+// own one group in stage 0 sit in the same warp, so a __syncwarp between the reads and the writes is all it takes.
+__device__ __forceinline__ int tma_slot(int k) { return k ^ (((k >> 4) & 7) << 1); }
+
+__device__ __forceinline__ void row_tile_tma_load(void* smem, unsigned long long* mbar, const void* tmap, u32 tile) {
+  const unsigned sm = (unsigned)__cvta_generic_to_shared(smem), mb = (unsigned)__cvta_generic_to_shared(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(65536u) : "memory");
+#pragma unroll
+    for (int j = 0; j < 2; ++j)  // two boxes of 16 x 256 residues
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+              sm + j * 32768u),
+          "l"(tmap), "r"(mb), "r"(0), "r"((int)(tile * 512u + j * 256u))
+          : "memory");
+  }
+  // every thread waits for the bytes (phase 0)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tTMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra TMA_DONE;\n\t"
+      "bra TMA_WAIT;\n\tTMA_DONE:\n\t}" ::"r"(mb)
+      : "memory");
+}
+#endif
+
 template <class Cfg, int R>
 __device__ __forceinline__ void gmem_load(const PassParams& prm, const u64* base, u32 row0, int k0, int logs,
                                           int p, u64 (&x)[R][Cfg::C]) {
+#if XNTT_PROBE_NOMEM
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < Cfg::C; ++c) x[r][c] = (u64)(threadIdx.x + 7 * r + c) * 0x9e3779b97f4a7c15ull + (u64)(k0 + p + row0 + logs);
+  (void)prm;
+  (void)base;
+  return;
+#endif
   if constexpr (Cfg::COL) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -243,6 +302,16 @@ __device__ __forceinline__ void gmem_load(const PassParams& prm, const u64* base
 template <class Cfg, int R>
 __device__ __forceinline__ void gmem_store(const PassParams& prm, u64* base, u32 row0, int k0, int logs, int p,
                                            const u64 (&x)[R][Cfg::C]) {
+#if XNTT_PROBE_NOMEM
+  // keeps the arithmetic alive, stores nothing (the value never occurs)
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < Cfg::C; ++c)
+      if (x[r][c] == 0x0123456789abcdefull) base[(u64)(k0 + (r << logs)) + p + c + row0] = x[r][c];
+  (void)prm;
+  return;
+#endif
   if constexpr (Cfg::MAP) {
     if (prm.peer_on != 0) {
       // fused exchange: the owner of output index k is rank k >> peer_bits; all ranks' buffers share one
@@ -493,7 +562,14 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
     const int k0 = (B << (LOGS + LOGR)) + i;
     u64 x[R][Cfg::C];
     if constexpr (J == 0) {
-      gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
+#if XNTT_TMA_ROWS && !defined(XNTT_HOST_EMU)
+      if constexpr (Cfg::TMA) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r][0] = sm[tma_slot(k0 + (r << LOGS))];
+        __syncwarp();  // stage 0 rewrites the tile in place, in the kernel's own swizzle (see tma_slot)
+      } else
+#endif
+        gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
       if constexpr (TWIST == kPreTwist || TWIST == kPrePointwise)
         apply_pre_twist<F, Cfg, R>(f, prm, x, k0, LOGS, row0 + (u32)(p * Cfg::C));
     } else {
@@ -558,7 +634,19 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
     const int k0 = (B << (LOGS + LOGR)) + i;
     u64 x[R][Cfg::C];
     if constexpr (J == 0) {
-      gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
+#if XNTT_TMA_ROWS && !defined(XNTT_HOST_EMU)
+      if constexpr (Cfg::TMA) {
+        // 8 consecutive residues per task: four 16-byte reads from the TMA-swizzled tile
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&sm[tma_slot(k0 + r)]);
+          x[r][0] = v.x;
+          x[r + 1][0] = v.y;
+        }
+        __syncwarp();
+      } else
+#endif
+        gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
       if constexpr (TWIST == kCompactTwist || TWIST == kFullTwist)
         apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
     } else {
@@ -654,6 +742,35 @@ __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_
   run_stages<F, Cfg, INVERSE, TWIST>(prm, sm, prm.src + sbase, prm.dst + dbase, col0, row0,
                                      std::make_integer_sequence<int, Cfg::NS>{});
 }
+#if XNTT_TMA_ROWS
+// Row pass of length 2^13 (one row per tile) with the tile staged by the TMA unit.  Same stages, same tables, same
+// results as pass_kernel<F, 13, 0, 1, false, ...>; only where stage 0 takes its input from differs.
+template <class F, bool INVERSE, int TWIST>
+__global__ void __launch_bounds__(kThreads, XNTT_MINB)
+    row_kernel_tma(const __grid_constant__ PassParams prm, const __grid_constant__ CUtensorMap tmap) {
+  typedef PassCfg<13, 0, 1, false, false, true> Cfg;
+  // the 128-byte swizzle is a function of the shared-memory address: the tile has to start on a 1024-byte boundary,
+  // which the launch only guarantees if we round up ourselves (1 KiB of slack is allocated for it); the mbarrier
+  // sits behind the tile
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + 65536);
+  auto* sm = reinterpret_cast<typename Slot<1>::type*>(smem_raw);
+  const u32 tile = blockIdx.x;
+  u64 sbase, dbase;
+  u32 col0 = 0, row0 = 0;
+  tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
+  if constexpr (TWIST == kPostTwist) {
+    for (int e = threadIdx.x * 8; e < Cfg::N * Cfg::W; e += kThreads * 8) {
+      const u32 row = row0 + (u32)(e >> Cfg::LOGN);
+      prefetch_l2(prm.pre_twist + (((u64)(row & prm.pre_rows_mask) << Cfg::LOGN) + (u64)(e & (Cfg::N - 1))));
+    }
+  }
+  row_tile_tma_load(smem_raw, mbar, &tmap, tile);
+  run_stages<F, Cfg, INVERSE, TWIST>(prm, sm, prm.src + sbase, prm.dst + dbase, col0, row0,
+                                     std::make_integer_sequence<int, Cfg::NS>{});
+}
+#endif
 #endif  // !XNTT_HOST_EMU
 
 }  // namespace xntt

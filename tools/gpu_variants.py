@@ -37,9 +37,13 @@ def timeit(fn, reps=30, warm=5):
 
 
 libs = sorted(glob.glob(os.path.join(ROOT, "sve-ntt_b200", "lib*", "libxntt.so")))
-cases = [(24, None, 1), (24, [12, 12], 1), (12, None, 4096), (20, None, 64), (28, None, 1)] + \
+cases = [(24, None, 1), (13, None, 2048), (26, None, 1)] + \
         [tuple(json.loads(a)) for a in sys.argv[1:]]
 res = {}
+gen = torch.Generator(device="cuda")
+gen.manual_seed(7)
+probe_in = torch.randint(0, 2**62, (1 << 24,), dtype=torch.int64, device="cuda", generator=gen)
+probe_ref = {}
 for path in libs:
     name = os.path.basename(os.path.dirname(path))
     lib = pkg.Library(path)
@@ -51,7 +55,18 @@ for path in libs:
     plan.forward(o.data_ptr(), d.data_ptr(), st)
     ok = bool(np.array_equal(o.cpu().numpy().view(np.uint64), orc.ntt_forward(a, P0, G0)))
     plan.close()
-    res[name] = {"parity": ok}
+    # the 2^24 plan (2^11 columns x 2^13 rows) of every variant against the product library, all words, both directions
+    plan = lib.plan(24)
+    f_out, i_out = torch.empty_like(probe_in), torch.empty_like(probe_in)
+    plan.forward(f_out.data_ptr(), probe_in.data_ptr(), st)
+    plan.inverse(i_out.data_ptr(), f_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    plan.close()
+    if name == "lib":
+        probe_ref["f"] = f_out.clone()
+    same = bool(torch.equal(f_out, probe_ref["f"])) if "f" in probe_ref else None
+    res[name] = {"parity": ok, "forward_2p24_equals_product": same, "roundtrip_2p24": bool(torch.equal(i_out, probe_in))}
+    print(name, res[name], flush=True)
     for L, splits, batch in cases:
         m = 1 << L
         try:
