@@ -281,7 +281,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -578,12 +578,39 @@ def bench_sharded(args, lib, torch, dist, rank, world, local_rank, log2_m):
             "one_gpu_same_workload": one_gpu,
             "speedup_vs_one_gpu_same_workload": value / one_gpu["value"],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
+class _StdoutGuard:
+    """Everything but the result goes to stderr: libraries (NCCL's version banner, for one) write to file descriptor 1
+    behind Python's back, and the contract is ONE JSON line on stdout.  emit() writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
+_OUT = None
+
+
+def emit(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global _OUT
     args = parse_args()
+    _OUT = _StdoutGuard()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -768,7 +795,7 @@ def main():
             "cpu_baseline": cpu, "cpu_baselines": cpu_all,
         }
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -33,7 +33,7 @@ for L in sizes:
     # every rank builds the same full input, keeps its column block
     gen = torch.Generator(device=dev)
     gen.manual_seed(1000 + L)
-    check = L <= 26
+    check = True  # every size: a 2^30 input plus its single-GPU transform is 16 GiB of the 180 GB per GPU
     if check:
         full = torch.randint(0, 2**62, (m,), dtype=torch.int64, device=dev, generator=gen)
         src = full.view(n0, n1)[:, rank * n1 // world:(rank + 1) * n1 // world].contiguous().view(-1)
