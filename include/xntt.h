@@ -44,7 +44,12 @@ enum {
   XNTT_ENABLE_INVERSE = 2,
   /* keep the six-step twiddles as two sqrt(M)-entry tables (two modular products per residue) even where
    * the planner would store the whole twiddle matrix (16 bytes per residue and direction, one product) */
-  XNTT_COMPACT_TABLES = 4
+  XNTT_COMPACT_TABLES = 4,
+  /* run the transform with Shoup ("fixed point") modular multiplication instead of Montgomery: the reference's
+   * alternative modmul type FixedPoint64SVE (include/sventt/modmul/sve/fixed-point-64.hpp:13-69).  Same results; legal
+   * for moduli below 2^62 (lazy values in [0, 4p)), where it needs 6 instead of 10 wide multiplies per butterfly.  Ignored
+   * (Montgomery kernels run) for larger moduli and for the production modulus, whose kernels have it baked in. */
+  XNTT_MODMUL_FIXED_POINT = 8
 };
 
 #define XNTT_MAX_SPLITS 4
@@ -59,7 +64,7 @@ typedef struct xntt_desc {
   uint32_t batch;          /* number of back-to-back transforms in one buffer (0 means 1)           */
   uint64_t inverse_factor; /* inverse output is divided by this (0 or 1: unscaled); the reference's */
                            /* inverse_factor layer argument (layer/sve/radix-eight.hpp:19)          */
-  uint32_t flags;          /* XNTT_ENABLE_* (neither bit = both, wrapper.hpp:34-35) | XNTT_COMPACT_TABLES */
+  uint32_t flags;          /* XNTT_ENABLE_* (neither bit = both, wrapper.hpp:34-35) | XNTT_COMPACT_TABLES | XNTT_MODMUL_FIXED_POINT */
   int32_t device;          /* CUDA device ordinal, -1 = current                                     */
   uint32_t n_splits;       /* 0 = let the planner decompose m; else the six-step decomposition      */
   uint32_t split_log2[XNTT_MAX_SPLITS]; /* m = prod 2^split_log2[i], outermost (column) first       */
@@ -85,6 +90,8 @@ uint64_t xntt_plan_m(const xntt_plan* plan);
 uint32_t xntt_plan_batch(const xntt_plan* plan);
 /* number of kernel launches one forward / inverse call makes (for bench accounting) */
 uint32_t xntt_plan_launches(const xntt_plan* plan, int inverse);
+/* arithmetic the pass kernels of this plan run: 0 = Montgomery (PAdic64), 1 = Shoup (FixedPoint64, XNTT_MODMUL_FIXED_POINT) */
+uint32_t xntt_plan_modmul(const xntt_plan* plan);
 /* fills out[0..n) with the log2 sizes of the passes, returns the pass count */
 uint32_t xntt_plan_splits(const xntt_plan* plan, uint32_t* out, uint32_t n);
 

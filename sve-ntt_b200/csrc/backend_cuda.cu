@@ -279,6 +279,11 @@ int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& pr
       e = inverse ? launch_inv_col(logn, prm, grid, st) : launch_fwd_col(logn, prm, grid, st);
     else
       e = inverse ? launch_inv_row(logn, prm, grid, st) : launch_fwd_row(logn, prm, grid, st);
+  } else if (prm.field.kind == kFieldShoup) {
+    if (col)
+      e = inverse ? launch_inv_col_sh(logn, prm, grid, st) : launch_fwd_col_sh(logn, prm, grid, st);
+    else
+      e = inverse ? launch_inv_row_sh(logn, prm, grid, st) : launch_fwd_row_sh(logn, prm, grid, st);
   } else {
     if (col)
       e = inverse ? launch_inv_col_rt(logn, prm, grid, st) : launch_fwd_col_rt(logn, prm, grid, st);
@@ -294,6 +299,10 @@ int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& pr
   do {                                           \
     if ((fc).p == kP0) {                         \
       typedef F0 F;                              \
+      const F f = make_field<F>(fc);             \
+      call;                                      \
+    } else if ((fc).kind == kFieldShoup) {       \
+      typedef FieldShoup F;                      \
       const F f = make_field<F>(fc);             \
       call;                                      \
     } else {                                     \

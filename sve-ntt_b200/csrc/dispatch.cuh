@@ -23,6 +23,11 @@ cudaError_t launch_fwd_row_rt(int logn, const PassParams& prm, unsigned grid, cu
 cudaError_t launch_inv_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+// runtime moduli below 2^62 with Shoup / FixedPoint64 arithmetic (field.cuh: FieldShoup)
+cudaError_t launch_fwd_row_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_row_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_col_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_col_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 
 #if XNTT_TMA_ROWS
 // Measured variant (XNTT_TMA_ROWS): tensor map over the source of a 2^13 row pass viewed as rows of 16 residues

@@ -223,6 +223,13 @@ struct FieldOps : K {
 
   // w' for a Montgomery-form w that was not precomputed (reference: precompute).
   __device__ __forceinline__ u64 companion(u64 w) const { return w * this->pinv(); }
+  // table entry of the twiddle whose Montgomery form is wm
+  __device__ __forceinline__ Tw make_tw(u64 wm) const {
+    Tw t;
+    t.w = wm;
+    t.wp = companion(wm);
+    return t;
+  }
 
   // lazy -> canonical
   __device__ __forceinline__ u64 canon(u64 v) const {
@@ -274,6 +281,59 @@ struct FieldOps : K {
 template <u64 P_>
 using Field = FieldOps<StaticModulus<P_>>;
 typedef FieldOps<RuntimeModulus> FieldRT;
+
+// ------------------------------------------------------------------------------------------------
+// Shoup ("fixed point") arithmetic for runtime moduli below 2^62 - the device twin of the reference's alternative
+// modmul type sventt::FixedPoint64SVE (include/sventt/modmul/sve/fixed-point-64.hpp:13-69):
+//   multiply(a, b, bp) : q = hi64(a * bp), c = a * b - q * N (low 64 bits), with bp = floor(b * 2^64 / N)
+// c lies in [0, 2N) for ANY 64-bit a.  With 4N < 2^64 the butterflies keep every intermediate in [0, 4N) (Harvey's
+// lazy butterflies: one conditional subtraction of 2N on the way in, none on the way out) - no carries to repair, and
+// the product needs 6 32x32->64 multiplies (4 for hi64(a * bp), 1 each for the two low products) instead of the 10 of
+// the lazy Montgomery butterfly above.  Twiddles are stored as (omega, floor(omega * 2^64 / N)) in the Tw slots.
+// The element-wise PAdic64 entry points of the C ABI (to_montgomery, multiply_normalize, the fused point-wise
+// product) keep their Montgomery meaning: those overloads are inherited from FieldRT.
+struct FieldShoup : FieldOps<RuntimeModulus> {
+  typedef FieldOps<RuntimeModulus> M;
+  using M::mont;  // mont(a, w, wp): Montgomery semantics (element-wise helpers)
+
+  // v in [0, 2m) -> [0, m)
+  __device__ __forceinline__ static u64 csub(u64 v, u64 m) {
+    const u64 t = v - m;
+    return v < m ? v : t;
+  }
+  // a * omega mod N, lazy: result in [0, 2N); a is any 64-bit value
+  __device__ __forceinline__ u64 mul_lazy(u64 a, u64 w, u64 wp) const { return a * w - mulhi64(a, wp) * this->p(); }
+  // canonical product with a table twiddle
+  __device__ __forceinline__ u64 mont(u64 a, Tw t) const { return csub(mul_lazy(a, t.w, t.wp), this->p()); }
+  // (omega, floor(omega * 2^64 / N)) from the Montgomery form wm = omega * 2^64 mod N: omega = wm * 2^-64, and the
+  // quotient Q of omega * 2^64 = Q * N + wm is exact, hence Q = -wm * N^-1 mod 2^64
+  __device__ __forceinline__ Tw make_tw(u64 wm) const {
+    Tw t;
+    t.w = M::mont(wm, 1ull, this->pinv());
+    t.wp = (0 - wm) * this->pinv();
+    return t;
+  }
+  // [0, 4N) -> [0, N)
+  __device__ __forceinline__ u64 canon(u64 v) const {
+    const u64 P = this->p();
+    return csub(csub(v, 2 * P), P);
+  }
+  // (x0, x1) <- (x0 + x1 * omega, x0 - x1 * omega), all values in [0, 4N)
+  __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, u64 w, u64 wp) const {
+    const u64 P2 = 2 * this->p();
+    const u64 a = csub(x0, P2), t = mul_lazy(x1, w, wp);
+    x0 = a + t;
+    x1 = a - t + P2;
+  }
+  __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, Tw t) const { ct_butterfly(x0, x1, t.w, t.wp); }
+  // omega = 1; x1 canonical (the networks canonicalise it first)
+  __device__ __forceinline__ void ct_butterfly_one(u64& x0, u64& x1) const {
+    const u64 P2 = 2 * this->p();
+    const u64 a = csub(x0, P2), t = x1;
+    x0 = a + t;
+    x1 = a - t + P2;
+  }
+};
 
 // The production prime of the reference README (README.md:19), C = 0x3917fffffff.
 typedef Field<kP0> F0;

@@ -52,10 +52,7 @@ __device__ __forceinline__ u32 table_exponent(u32 idx, int kind, int logn, int s
 
 template <class F>
 __device__ __forceinline__ Tw table_entry(const F& f, u32 idx, int kind, int logn, int shift, const PowTable& t) {
-  Tw r;
-  r.w = pow_mont<F>(f, t, table_exponent(idx, kind, logn, shift));
-  r.wp = f.companion(r.w);
-  return r;
+  return f.make_tw(pow_mont<F>(f, t, table_exponent(idx, kind, logn, shift)));
 }
 
 // PAdic64::to_montgomery (p-adic-64.hpp:19-22): a * 2^64 mod P, r2 = 2^128 mod P

@@ -51,7 +51,12 @@ struct FieldConsts {
   u64 p;     // modulus
   u64 pinv;  // p^-1 mod 2^64
   u64 one;   // 2^64 mod p
+  // arithmetic of the pass kernels: 0 = Montgomery (PAdic64), 1 = Shoup / FixedPoint64 (moduli below 2^62 only;
+  // twiddle tables then hold (omega, floor(omega * 2^64 / p)) instead of the Montgomery pair)
+  u32 kind;
+  u32 reserved_;
 };
+constexpr u32 kFieldMontgomery = 0, kFieldShoup = 1;
 
 struct PassParams {
   const u64* src;

@@ -525,12 +525,19 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   pl->shard_rank = d->shard_rank;
   const u64 finv = h_inv(f, p);
   pl->scale_on = (f != 1);
-  pl->scale.w = h_to_mont(finv, p);
-  pl->scale.wp = pl->scale.w * h_montgomery_inverse(p);
   pl->r2 = h_to_mont(h_to_mont(1, p), p);
   pl->field.p = p;
   pl->field.pinv = h_montgomery_inverse(p);
   pl->field.one = h_to_mont(1, p);
+  // FixedPoint64 (Shoup) arithmetic where it is legal: 4p < 2^64; the production modulus has its own kernels
+  pl->field.kind = ((d->flags & XNTT_MODMUL_FIXED_POINT) && p != kP0 && (p >> 62) == 0) ? kFieldShoup : kFieldMontgomery;
+  if (pl->field.kind == kFieldShoup) {
+    pl->scale.w = finv;  // (omega, floor(omega * 2^64 / p))
+    pl->scale.wp = (u64)(((u128)finv << 64) / p);
+  } else {
+    pl->scale.w = h_to_mont(finv, p);
+    pl->scale.wp = pl->scale.w * h_montgomery_inverse(p);
+  }
 
   int dev = d->device;
   if (dev < 0) {
@@ -684,6 +691,7 @@ int xntt_plan_destroy(xntt_plan* pl) {
 uint64_t xntt_plan_m(const xntt_plan* pl) { return pl ? (1ull << pl->log2_m) : 0; }
 uint32_t xntt_plan_batch(const xntt_plan* pl) { return pl ? pl->batch : 0; }
 uint32_t xntt_plan_launches(const xntt_plan* pl, int) { return pl ? (uint32_t)pl->passes.size() : 0; }
+uint32_t xntt_plan_modmul(const xntt_plan* pl) { return pl ? pl->field.kind : 0; }
 uint32_t xntt_plan_splits(const xntt_plan* pl, uint32_t* out, uint32_t n) {
   if (!pl) return 0;
   for (uint32_t i = 0; out && i < n && i < pl->passes.size(); ++i) out[i] = (uint32_t)pl->passes[i].logn;

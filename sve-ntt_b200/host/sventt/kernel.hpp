@@ -41,6 +41,8 @@ class IterativeNTT {
     ((f = modulus_type::multiply(f, layer_types::get_inverse_factor())), ...);
     return f;
   }
+  // every layer carries the FixedPoint64 tag: run the Shoup kernels (wrapper.hpp sets XNTT_MODMUL_FIXED_POINT)
+  static constexpr bool all_fixed_point() { return (layer_types::all_fixed_point() && ...); }
   // one contiguous transform of length m: a single planner unit
   static void append_splits(std::vector<std::uint32_t>& out) { out.push_back(detail::log2_exact(m)); }
 
@@ -65,6 +67,7 @@ class RecursiveNTT {
   static constexpr std::uint64_t get_inverse_factor() {
     return modulus_type::multiply(layer_type::get_inverse_factor(), inner_kernel_type::get_inverse_factor());
   }
+  static constexpr bool all_fixed_point() { return layer_type::all_fixed_point() && inner_kernel_type::all_fixed_point(); }
   static void append_splits(std::vector<std::uint32_t>& out) {
     if constexpr (layer_type::is_six_step()) {
       // (blocked) six-step: n0 = radix column transforms, then the inner kernel on every row

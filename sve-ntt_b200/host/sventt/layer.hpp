@@ -33,6 +33,7 @@ class RadixLayer {
   static constexpr std::uint64_t get_n() { return n; }
   static constexpr std::uint64_t get_inverse_factor() { return inverse_factor; }
   static constexpr bool is_six_step() { return false; }
+  static constexpr bool all_fixed_point() { return modmul_type::is_fixed_point; }
   static_assert(n >= radix, "sub-transform shorter than the radix");
   static_assert(m % n == 0, "n must divide m");
   // radix-two.hpp:208-211: only a terminal layer (n == radix) may carry the inverse factor
@@ -68,6 +69,7 @@ class GenericLayer {
   static constexpr std::uint64_t get_radix() { return inner_kernel_type::get_m(); }
   static constexpr std::uint64_t get_inverse_factor() { return inner_kernel_type::get_inverse_factor(); }
   static constexpr bool is_six_step() { return true; }
+  static constexpr bool all_fixed_point() { return modmul_type::is_fixed_point && inner_kernel_type::all_fixed_point(); }
   static_assert(m % inner_kernel_type_::get_m() == 0);
 };
 template <class modmul_type, std::uint64_t m, class inner_kernel_type, std::uint64_t buffer_padding_elements = 0,

@@ -18,6 +18,7 @@ class PAdic64 {
 
  public:
   using modulus_type = modulus_type_;
+  static constexpr bool is_fixed_point = false;
 
   // b * 2^64 mod N   (p-adic-64.hpp:19-22)
   static constexpr std::uint64_t to_montgomery(std::uint64_t b) {
@@ -54,15 +55,17 @@ class PAdic64 {
 
 // sventt::FixedPoint64<modulus_type> - the Shoup-style alternative modmul tag
 // (include/sventt/modmul/{scalar,sve}/fixed-point-64.hpp): to/from_montgomery are the identity,
-// precompute(b) = floor(b * 2^64 / N), multiply(a, b, bp) = a * b mod N.  As a layer tag it selects the
-// same device kernels (the transform computed is the same function); the scalar helpers follow the
-// reference so that mixed-tag compositions (tests/ntt-tests/iterative-scalar-radix2-two10.hpp) compile.
+// precompute(b) = floor(b * 2^64 / N), multiply(a, b, bp) = a * b mod N.  A composition whose layers ALL carry this
+// tag runs the device kernels with Shoup arithmetic (csrc/field.cuh: FieldShoup, XNTT_MODMUL_FIXED_POINT) when the
+// modulus is below 2^62; a composition that mixes it with PAdic64 (tests/ntt-tests/iterative-scalar-radix2-two10.hpp)
+// or a larger modulus runs the Montgomery kernels - the transform computed is the same function either way.
 template <class modulus_type_>
 class FixedPoint64 {
   using u128 = unsigned __int128;
 
  public:
   using modulus_type = modulus_type_;
+  static constexpr bool is_fixed_point = true;
   static constexpr std::uint64_t to_montgomery(std::uint64_t b) { return b; }
   static constexpr std::uint64_t from_montgomery(std::uint64_t b) { return b; }
   static constexpr std::uint64_t precompute(std::uint64_t b) {

@@ -75,6 +75,7 @@ class NTT {
     d.flags = (enable_forward ? static_cast<std::uint32_t>(XNTT_ENABLE_FORWARD) : 0u) |
               (enable_inverse ? static_cast<std::uint32_t>(XNTT_ENABLE_INVERSE) : 0u);
     if (d.flags == 0) d.flags = XNTT_ENABLE_FORWARD | XNTT_ENABLE_INVERSE;
+    if constexpr (kernel_type::all_fixed_point()) d.flags |= XNTT_MODMUL_FIXED_POINT;  // FixedPoint64 layers throughout
     d.device = device;
     std::vector<std::uint32_t> splits;
     kernel_type::append_splits(splits);
@@ -130,6 +131,8 @@ class NTT {
   }
   const xntt_plan* plan() const { return plan_; }
   xntt_mgpu* mgpu() const { return mgpu_; }
+  // 1 when the device kernels run FixedPoint64 (Shoup) arithmetic, 0 for PAdic64 (Montgomery)
+  std::uint32_t get_modmul_kind() const { return plan_ ? xntt_plan_modmul(plan_) : 0u; }
   // multi-GPU plans, device-resident shards (layouts: include/xntt.h, xntt_mgpu_forward); asynchronous
   void compute_forward_shards(std::uint64_t* const* dst, const std::uint64_t* const* src) const {
     detail::check(mgpu_ ? xntt_mgpu_forward(mgpu_, dst, src) : XNTT_ERR_STATE, "compute_forward_shards");

@@ -55,6 +55,21 @@ using kernel_type =
                  RadixFourScalarLayer<pa, m, one << 8>, RadixFourScalarLayer<fp, m, one << 6>,
                  RadixEightScalarLayer<pa, m, one << 4>, RadixTwoScalarLayer<fp, m, one << 1, m>>;
 }  // namespace it_mixed
+// ---- every layer FixedPoint64 (modmul/sve/fixed-point-64.hpp): the device runs the Shoup kernels
+namespace it_fixed {
+constexpr std::uint64_t m{one << 12};
+using fp = FixedPoint64SVE<modulus_type>;
+using kernel_type = IterativeNTT<modulus_type, m, RadixEightSVELayer<fp, m, one << 12>, RadixEightSVELayer<fp, m, one << 9>,
+                                 RadixEightSVELayer<fp, m, one << 6>, RadixEightSVELayer<fp, m, one << 3, m>>;
+}  // namespace it_fixed
+namespace rec_fixed {  // four-step 2^9 x 2^6 with FixedPoint64 layers
+constexpr std::uint64_t m{one << 15}, n0{one << 9}, n1{one << 6};
+using fp = FixedPoint64SVE<modulus_type>;
+using inner0 = IterativeNTT<modulus_type, n0, RadixEightSVELayer<fp, n0, n0>, RadixEightSVELayer<fp, n0, (n0 >> 3)>,
+                            RadixEightSVELayer<fp, n0, (n0 >> 6)>>;
+using inner1 = IterativeNTT<modulus_type, n1, RadixEightSVELayer<fp, n1, n1>, RadixEightSVELayer<fp, n1, (n1 >> 3), m>>;
+using kernel_type = RecursiveNTT<modulus_type, m, GenericSVELayer<fp, m, inner0, 0, 1>, inner1, true>;
+}  // namespace rec_fixed
 // ---- tests/ntt-tests/iterative-sve-radix4-two12.hpp
 namespace it_r4 {
 constexpr std::uint64_t m{one << 12};
@@ -238,6 +253,17 @@ int main(int argc, char** argv) {
   try {
     both<it_r2::kernel_type>("iterative, SVE, radix-2");
     both<it_mixed::kernel_type>("iterative, scalar, mixed modmul tags");
+    both<it_fixed::kernel_type>("iterative, FixedPoint64 layers (Shoup kernels)");
+    both<rec_fixed::kernel_type>("four-step, FixedPoint64 layers (Shoup kernels)");
+    {
+      static_assert(it_fixed::kernel_type::all_fixed_point() && rec_fixed::kernel_type::all_fixed_point());
+      static_assert(!it_mixed::kernel_type::all_fixed_point() && !it_r8::kernel_type::all_fixed_point());
+      const NTT<it_fixed::kernel_type> shoup;
+      const NTT<it_mixed::kernel_type> mixed;
+      const bool tag_ok = shoup.get_modmul_kind() == 1 && mixed.get_modmul_kind() == 0;
+      std::printf("%-53s %s\n", "FixedPoint64 tag selects the Shoup kernels", tag_ok ? "ok" : "MISMATCH");
+      failures += !tag_ok;
+    }
     both<it_r4::kernel_type>("iterative, SVE, radix-4");
     both<it_r8::kernel_type>("iterative, SVE, radix-8");
     both<it_r248::kernel_type>("iterative, scalar, radix-2,4,8");

@@ -135,6 +135,7 @@ static int emu_launch(const PassParams& prm, unsigned grid) {
   // same choice as backend_cuda.cu: baked-in modulus for kP0, runtime modulus otherwise
   if (g_map) return prm.field.p == kP0 ? emu_launch2<F0, LOGN, COL, INV, true>(prm, grid) : 1;
   if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV, false>(prm, grid);
+  if (prm.field.kind == kFieldShoup) return emu_launch2<FieldShoup, LOGN, COL, INV, false>(prm, grid);
   return emu_launch2<FieldRT, LOGN, COL, INV, false>(prm, grid);
 }
 
@@ -228,6 +229,10 @@ int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& pr
   do {                               \
     if ((fc).p == kP0) {             \
       typedef F0 F;                  \
+      const F f = make_field<F>(fc); \
+      call;                          \
+    } else if ((fc).kind == kFieldShoup) { \
+      typedef FieldShoup F;          \
       const F f = make_field<F>(fc); \
       call;                          \
     } else {                         \

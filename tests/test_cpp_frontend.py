@@ -22,7 +22,7 @@ def test_reference_compositions_on_emulator():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ALL OK" in out.stdout and "MISMATCH" not in out.stdout
-    assert out.stdout.count(" ok") == 22
+    assert out.stdout.count(" ok") == 27
 
 
 @pytest.mark.gpu
@@ -31,7 +31,7 @@ def test_reference_compositions_on_gpu():
     out = subprocess.run([exe, "--big"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ALL OK" in out.stdout and "MISMATCH" not in out.stdout
-    assert out.stdout.count(" ok") == 26
+    assert out.stdout.count(" ok") == 31
 
 
 def test_kinnaes_class_on_emulator():

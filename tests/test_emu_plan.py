@@ -444,3 +444,49 @@ def test_mgpu_argument_checks(emu):
         emu.mgpu(16, [0, 1], modulus=0xFFFFFFFF00000001, generator=7)  # address-mapped kernels: production prime only
     with _pt.raises(Exception):
         emu.mgpu(12, [0, 1])  # single-pass size: nothing to exchange
+
+
+SHOUP_MODULI = [(N, g) for N, g in OTHER_MODULI if N < (1 << 62)]
+
+
+@pytest.mark.parametrize("N,g", SHOUP_MODULI)
+def test_fixed_point_modmul(emu, oracle, N, g):
+    """XNTT_MODMUL_FIXED_POINT: Shoup arithmetic (FixedPoint64SVE, modmul/sve/fixed-point-64.hpp:13-69) for moduli below
+    2^62 - same words as the oracle, every pass kind (compact / whole-matrix twiddles, scaled inverse, batches)."""
+    for L, splits, batch, kw in [(1, None, 1, {}), (3, None, 5, {}), (7, None, 1, {}), (10, None, 3, {}),
+                                 (13, None, 1, {}), (15, None, 1, {}), (13, [9, 4], 1, {}),
+                                 (16, [5, 5, 6], 1, {}), (14, None, 1, {"compact_tables": True}),
+                                 (12, None, 2, {"inverse_factor": 12345})]:
+        if (N - 1) % (1 << L):
+            continue
+        m = 1 << L
+        a = oracle.fill_xorshift(m * batch, SEED + L, N)
+        plan = emu.plan(L, modulus=N, generator=g, splits=splits, batch=batch, fixed_point=True, **kw)
+        assert plan.modmul == 1
+        out = np.empty_like(a)
+        plan.forward(out.ctypes.data, a.ctypes.data)
+        for b in range(batch):
+            assert np.array_equal(out[b * m:(b + 1) * m], oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), N, g)), (hex(N), L)
+        back = np.empty_like(a)
+        plan.inverse(back.ctypes.data, out.ctypes.data)
+        f = kw.get("inverse_factor", m)
+        scale = np.full_like(a, (m * pow(f, -1, N)) % N)
+        assert np.array_equal(back, oracle.pointwise_mul(a, scale, N)), (hex(N), L)
+        # fused point-wise product keeps its Montgomery (PAdic64) meaning on such a plan
+        if L >= 3 and batch == 1:
+            bm = np.empty_like(a)
+            plan.to_montgomery(bm.ctypes.data, a.ctypes.data, m)
+            fm = np.empty_like(a)
+            plan.forward_multiply(fm.ctypes.data, a.ctypes.data, bm.ctypes.data)
+            assert np.array_equal(fm, oracle.pointwise_mul(out, a, N)), (hex(N), L)
+
+
+def test_fixed_point_flag_is_ignored_where_illegal(emu, oracle):
+    """4p must fit 64 bits: for 62-bit-plus moduli and the production modulus the flag leaves the Montgomery kernels."""
+    for N, g in [(P0, G0), (0xFFFFFFFF00000001, 7), (0xA3B25F400C7A8001, 5), (0x41D33D0D1FBF8001, 6)]:
+        plan = emu.plan(10, modulus=N, generator=g, fixed_point=True)
+        assert plan.modmul == 0
+        a = oracle.fill_xorshift(1 << 10, SEED, N)
+        out = np.empty_like(a)
+        plan.forward(out.ctypes.data, a.ctypes.data)
+        assert np.array_equal(out, oracle.ntt_forward(a, N, g))

@@ -503,6 +503,40 @@ def test_other_moduli(cuda_lib, oracle, N, g):
         plan.close()
 
 
+@pytest.mark.parametrize("N,g", [(N, g) for N, g in OTHER_MODULI if N < (1 << 62)])
+def test_fixed_point_modmul(cuda_lib, oracle, N, g):
+    """XNTT_MODMUL_FIXED_POINT: the Shoup kernels (FixedPoint64SVE, modmul/sve/fixed-point-64.hpp:13-69; csrc/field.cuh
+    FieldShoup) for moduli below 2^62 against the oracle - every pass kind, scaled inverse, batches, 2^24."""
+    import torch
+    for L, splits, batch, kw in [(1, None, 1, {}), (3, None, 5, {}), (7, None, 1, {}), (10, None, 3, {}), (13, None, 2, {}),
+                                 (15, None, 1, {}), (13, [9, 4], 1, {}), (16, [5, 5, 6], 1, {}),
+                                 (14, None, 1, {"compact_tables": True}), (12, None, 2, {"inverse_factor": 12345}),
+                                 (20, None, 1, {}), (24, None, 1, {})]:
+        if (N - 1) % (1 << L):
+            continue
+        m = 1 << L
+        a = oracle.fill_xorshift(m * batch, SEED + L, N)
+        plan = cuda_lib.plan(L, modulus=N, generator=g, splits=splits, batch=batch, fixed_point=True, **kw)
+        assert plan.modmul == 1
+        src = dev(a)
+        dst = torch.full_like(src, 0x5555555555555555)
+        plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+        got = host(dst)
+        for b in range(batch):
+            assert np.array_equal(got[b * m:(b + 1) * m], oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), N, g)), (hex(N), L, b)
+        back = torch.empty_like(src)
+        plan.inverse(back.data_ptr(), dst.data_ptr(), stream())
+        f = kw.get("inverse_factor", m)
+        scale = np.full_like(a, (m * pow(f, -1, N)) % N)
+        assert np.array_equal(host(back), oracle.pointwise_mul(a, scale, N)), (hex(N), L)
+        if batch == 1 and L >= 3:
+            bm, fm = torch.empty_like(src), torch.empty_like(src)
+            plan.to_montgomery(bm.data_ptr(), src.data_ptr(), m, stream())
+            plan.forward_multiply(fm.data_ptr(), src.data_ptr(), bm.data_ptr(), stream())
+            assert np.array_equal(host(fm), oracle.pointwise_mul(got, a, N)), (hex(N), L)
+        plan.close()
+
+
 @pytest.mark.parametrize("L,splits,N,g", [(14, None, P0, G0), (13, [9, 4], 0x3A00000000000001, 3), (20, None, P0, G0),
                                          (24, None, P0, G0)])
 def test_fused_forward_multiply(cuda_lib, oracle, L, splits, N, g):
