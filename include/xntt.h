@@ -166,7 +166,7 @@ int xntt_shard_inverse_rows_peer(const xntt_plan* plan, uint64_t* const* peers, 
  * and orders the single exchange of the six-step split with events.  It stands in for the one call the reference makes
  * for the whole composition, RecursiveNTT<..., (Blocked)GenericSVELayer, inner, true>::compute_forward / compute_inverse
  * (include/sventt/kernel/recursive.hpp:48-84, 103-140), whose global transposition (layer/sve/generic.hpp:112-161) is the
- * exchange.  desc is an ordinary transform descriptor (batch <= 1, shard fields unused, production modulus); devices[]
+ * exchange.  desc is an ordinary transform descriptor (batch <= 1, shard fields unused, any modulus); devices[]
  * lists n_devices (2, 4 or 8) CUDA ordinals, rank r = devices[r].  The same ordinal may appear more than once: all ranks
  * then share that GPU (how the sharded kernels are parity-tested on a single-GPU box).
  *   xntt_mgpu_forward / _inverse : device-resident shards.  Time domain: rank r holds the column block

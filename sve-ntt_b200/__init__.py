@@ -284,13 +284,14 @@ class MultiGpu:
     """xntt_mgpu: one transform over several GPUs of this process (C++-hosted exchange, include/xntt.h)."""
 
     def __init__(self, library, log2_m, devices, modulus=P0, generator=G0, inverse_factor=None, splits=None,
-                 forward=True, inverse=True):
+                 forward=True, inverse=True, fixed_point=False):
         self.L = library
         d = Desc()
         d.modulus, d.generator = modulus, generator
         d.log2_m, d.batch = log2_m, 1
         d.inverse_factor = (1 << log2_m) if inverse_factor is None else inverse_factor
-        d.flags = (ENABLE_FORWARD if forward else 0) | (ENABLE_INVERSE if inverse else 0)
+        d.flags = (ENABLE_FORWARD if forward else 0) | (ENABLE_INVERSE if inverse else 0) | \
+            (MODMUL_FIXED_POINT if fixed_point else 0)
         d.device = -1
         if splits:
             d.n_splits = len(splits)

@@ -266,14 +266,22 @@ int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& pr
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (map) {
-    if (prm.field.p != kP0) {
-      g_err = "address-mapped kernels are built for the production modulus only";
-      return 1;
+    if (prm.field.p == kP0) {
+      if (col)
+        e = inverse ? launch_inv_col_map(logn, prm, grid, st) : launch_fwd_col_map(logn, prm, grid, st);
+      else
+        e = inverse ? launch_inv_row_map(logn, prm, grid, st) : launch_fwd_row_map(logn, prm, grid, st);
+    } else if (prm.field.kind == kFieldShoup) {
+      if (col)
+        e = inverse ? launch_inv_col_map_sh(logn, prm, grid, st) : launch_fwd_col_map_sh(logn, prm, grid, st);
+      else
+        e = inverse ? launch_inv_row_map_sh(logn, prm, grid, st) : launch_fwd_row_map_sh(logn, prm, grid, st);
+    } else {
+      if (col)
+        e = inverse ? launch_inv_col_map_rt(logn, prm, grid, st) : launch_fwd_col_map_rt(logn, prm, grid, st);
+      else
+        e = inverse ? launch_inv_row_map_rt(logn, prm, grid, st) : launch_fwd_row_map_rt(logn, prm, grid, st);
     }
-    if (col)
-      e = inverse ? launch_inv_col_map(logn, prm, grid, st) : launch_fwd_col_map(logn, prm, grid, st);
-    else
-      e = inverse ? launch_inv_row_map(logn, prm, grid, st) : launch_fwd_row_map(logn, prm, grid, st);
   } else if (prm.field.p == kP0) {
     if (col)
       e = inverse ? launch_inv_col(logn, prm, grid, st) : launch_fwd_col(logn, prm, grid, st);

@@ -14,11 +14,20 @@ cudaError_t launch_fwd_row(int logn, const PassParams& prm, unsigned grid, cudaS
 cudaError_t launch_inv_row(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
-// kP0 kernels with generalised src/dst address maps (passes next to the all-to-all of a sharded plan)
+// kernels with generalised src/dst address maps (passes next to the all-to-all of a sharded plan): production modulus
 cudaError_t launch_fwd_row_map(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_row_map(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col_map(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col_map(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+// ... and for runtime moduli (Montgomery / Shoup)
+cudaError_t launch_fwd_row_map_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_row_map_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_col_map_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_col_map_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_row_map_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_row_map_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_col_map_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_col_map_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);

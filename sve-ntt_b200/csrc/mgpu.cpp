@@ -235,7 +235,6 @@ int xntt_mgpu_create(xntt_mgpu** out, const xntt_desc* desc, const int32_t* devi
   *out = nullptr;
   if (n_devices < 2 || n_devices > 8 || (n_devices & (n_devices - 1))) return XNTT_ERR_INVALID;
   if (desc->batch > 1 || desc->shard_count > 1) return XNTT_ERR_INVALID;
-  if (desc->modulus != kP0) return XNTT_ERR_UNSUPPORTED;  // the address-mapped kernels are built for the production prime
   for (u32 i = 0; i < n_devices; ++i)
     if (devices[i] < 0) return XNTT_ERR_INVALID;
   xntt_mgpu* g = new (std::nothrow) xntt_mgpu;

@@ -133,7 +133,11 @@ static bool g_map = false;
 template <int LOGN, bool COL, bool INV>
 static int emu_launch(const PassParams& prm, unsigned grid) {
   // same choice as backend_cuda.cu: baked-in modulus for kP0, runtime modulus otherwise
-  if (g_map) return prm.field.p == kP0 ? emu_launch2<F0, LOGN, COL, INV, true>(prm, grid) : 1;
+  if (g_map) {
+    if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV, true>(prm, grid);
+    if (prm.field.kind == kFieldShoup) return emu_launch2<FieldShoup, LOGN, COL, INV, true>(prm, grid);
+    return emu_launch2<FieldRT, LOGN, COL, INV, true>(prm, grid);
+  }
   if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV, false>(prm, grid);
   if (prm.field.kind == kFieldShoup) return emu_launch2<FieldShoup, LOGN, COL, INV, false>(prm, grid);
   return emu_launch2<FieldRT, LOGN, COL, INV, false>(prm, grid);

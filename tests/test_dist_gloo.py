@@ -54,7 +54,8 @@ def _worker(rank, world, port, log2_m, splits, modulus, emu_path, q):
 
 @pytest.mark.parametrize("world,log2_m,splits,modulus", [
     (2, 14, [7, 7], None), (4, 16, [6, 5, 5], None), (2, 15, None, None), (4, 18, [7, 11], None),
-    (2, 14, [7, 7], (0x3A00000000000001, 3)),  # other moduli take the whole-block path
+    (2, 14, [7, 7], (0x3A00000000000001, 3)),  # runtime-modulus address-mapped kernels
+    (4, 16, [6, 5, 5], (0xFFFFFFFF00000001, 7)),
 ])
 def test_sharded_transform_over_gloo(emu, world, log2_m, splits, modulus):
     ctx = mp.get_context("spawn")

@@ -441,9 +441,26 @@ def test_mgpu_argument_checks(emu):
         with _pt.raises(Exception):
             emu.mgpu(16, devs)
     with _pt.raises(Exception):
-        emu.mgpu(16, [0, 1], modulus=0xFFFFFFFF00000001, generator=7)  # address-mapped kernels: production prime only
-    with _pt.raises(Exception):
         emu.mgpu(12, [0, 1])  # single-pass size: nothing to exchange
+
+
+@pytest.mark.parametrize("N,g,fixed", [(0xFFFFFFFF00000001, 7, False), (0x3A00000000000001, 3, False),
+                                       (0x3A00000000000001, 3, True), (0x0003F00000000001, 11, True)])
+def test_mgpu_other_moduli(emu, oracle, N, g, fixed):
+    """Sharded plans are not tied to the production prime: the address-mapped (exchange-side) kernels exist for the
+    runtime-modulus Montgomery and Shoup flavours too."""
+    for L, splits, G in [(14, None, 2), (16, [6, 5, 5], 4)]:
+        m = 1 << L
+        a = oracle.fill_xorshift(m, SEED + L, N)
+        want = oracle.ntt_forward(a, N, g)
+        mg = emu.mgpu(L, list(range(G)), splits=splits, modulus=N, generator=g, fixed_point=fixed)
+        got = np.empty_like(a)
+        mg.forward_host(got.ctypes.data, a.ctypes.data)
+        assert np.array_equal(got, want), (hex(N), L, G)
+        back = np.empty_like(a)
+        mg.inverse_host(back.ctypes.data, got.ctypes.data)
+        assert np.array_equal(back, a)
+        mg.close()
 
 
 SHOUP_MODULI = [(N, g) for N, g in OTHER_MODULI if N < (1 << 62)]

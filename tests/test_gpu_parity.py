@@ -405,6 +405,24 @@ def test_sharded_plan_on_one_gpu(cuda_lib, oracle, L, G, splits):
     mg.close()
 
 
+@pytest.mark.parametrize("N,g,fixed", [(0xFFFFFFFF00000001, 7, False), (0x3A00000000000001, 3, False),
+                                       (0x3A00000000000001, 3, True)])
+def test_sharded_plan_other_moduli_on_one_gpu(cuda_lib, oracle, N, g, fixed):
+    """The sharded path with runtime moduli (Montgomery and Shoup address-mapped kernels), all ranks on device 0."""
+    for L, G, splits in [(20, 4, None), (21, 2, [7, 7, 7])]:
+        m = 1 << L
+        a = oracle.fill_xorshift(m, SEED + L, N)
+        want = oracle.ntt_forward(a, N, g)
+        mg = cuda_lib.mgpu(L, [0] * G, splits=splits, modulus=N, generator=g, fixed_point=fixed)
+        out = np.empty_like(a)
+        mg.forward_host(out.ctypes.data, a.ctypes.data)
+        assert np.array_equal(out, want), (hex(N), L, G)
+        back = np.empty_like(a)
+        mg.inverse_host(back.ctypes.data, out.ctypes.data)
+        assert np.array_equal(back, a)
+        mg.close()
+
+
 @pytest.mark.parametrize("L,G,K,splits", [(20, 2, 4, None), (22, 4, 2, None), (21, 8, 1, [7, 7, 7]), (24, 8, 4, None)])
 def test_sharded_chunked_exchange_on_one_gpu(cuda_lib, oracle, L, G, K, splits):
     """The NCCL-pipelined variant's kernels (column pass per chunk into message layout, tiled row half) with all ranks
