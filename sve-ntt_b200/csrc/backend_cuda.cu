@@ -373,8 +373,12 @@ int launch_transpose(u64* dst, const u64* src, u64 rows, u64 cols, u64 ld_dst, u
     attr_done.store(true, std::memory_order_release);
   }
   if (dst == src) {
-    const dim3 grid2(p.tiles_c, p.tiles_c);
-    transpose_inplace_kernel<<<grid2, kTrThreads, 2 * kTrSmemWords * sizeof(u64), (cudaStream_t)stream>>>(p);
+    const u64 pairs = (u64)p.tiles_c * (p.tiles_c + 1) / 2;  // upper triangle of the tile grid
+    if (pairs > 0x7fffffffull) {
+      g_err = "matrix too large for the in-place transposition";
+      return 1;
+    }
+    transpose_inplace_kernel<<<(unsigned)pairs, kTrThreads, 2 * kTrSmemWords * sizeof(u64), (cudaStream_t)stream>>>(p);
   } else {
     transpose_kernel<<<(unsigned)(tiles_r * p.tiles_c), kTrThreads, kTrSmemWords * sizeof(u64),
                        (cudaStream_t)stream>>>(p);
