@@ -44,6 +44,37 @@ for L, splits, batch, compact in cases:
     print(L, plan.splits, batch, "compact" if compact else "matrix", "ok" if ok else "MISMATCH", flush=True)
     bad += 0 if ok else 1
     plan.close()
+# runtime-modulus kernels (Montgomery and Shoup) and the multi-GPU plan with every rank on this device (peer stores,
+# address-mapped passes)
+for N, g, fixed in [(0xFFFFFFFF00000001, 7, False), (0x3A00000000000001, 3, True)]:
+    for L, splits in [(13, None), (16, [5, 5, 6])]:
+        a = orc.fill_xorshift(1 << L, 5 + L, N)
+        plan = lib.plan(L, modulus=N, generator=g, splits=splits, fixed_point=fixed)
+        d = torch.from_numpy(a.view(np.int64)).cuda()
+        o = torch.empty_like(d)
+        plan.forward(o.data_ptr(), d.data_ptr(), st)
+        torch.cuda.synchronize()
+        ok = bool(np.array_equal(o.cpu().numpy().view(np.uint64), orc.ntt_forward(a, N, g)))
+        print(hex(N), L, "shoup" if plan.modmul else "montgomery", "ok" if ok else "MISMATCH", flush=True)
+        bad += 0 if ok else 1
+        plan.close()
+for L, G, splits, N, g in [(16, 4, None, P0, G0), (15, 8, [3, 12], P0, G0), (18, 2, [6, 6, 6], P0, G0),
+                           (16, 4, None, 0x3A00000000000001, 3)]:
+    a = orc.fill_xorshift(1 << L, 77 + L, N)
+    mg = lib.mgpu(L, [0] * G, splits=splits, modulus=N, generator=g)
+    out, back = np.empty_like(a), np.empty_like(a)
+    mg.forward_host(out.ctypes.data, a.ctypes.data)
+    mg.inverse_host(back.ctypes.data, out.ctypes.data)
+    ok = bool(np.array_equal(out, orc.ntt_forward(a, N, g))) and bool(np.array_equal(back, a))
+    print("mgpu", L, G, splits, hex(N), "ok" if ok else "MISMATCH", flush=True)
+    bad += 0 if ok else 1
+    mg.close()
+# in-place and out-of-place transposition
+q = torch.arange(200 * 200, dtype=torch.int64, device="cuda").view(200, 200).clone()
+want = q.t().contiguous()
+lib.transpose(q.data_ptr(), q.data_ptr(), 200, 200, 200, 200, st)
+torch.cuda.synchronize()
+bad += 0 if torch.equal(q, want) else 1
 # stand-alone kernels
 t = torch.empty((200, 130), dtype=torch.int64, device="cuda")
 s = torch.arange(130 * 200, dtype=torch.int64, device="cuda").view(130, 200)
