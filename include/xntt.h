@@ -72,7 +72,8 @@ typedef struct xntt_desc {
   /* [shard_rank * n1 / shard_count, ...) of the first split's n0 x n1 matrix. 0/0 = not sharded.   */
   uint32_t shard_count;
   uint32_t shard_rank;
-  /* budget for whole twiddle matrices (16 bytes per residue and direction), MiB per plan; 0 = default (512).  */
+  /* budget for whole twiddle matrices (16 bytes per residue and direction), MiB per plan; 0 = default: 512, plus the */
+  /* m-entry matrix of the outermost pass of a three-pass plan while it takes at most a quarter of the free memory.  */
   /* A matrix that does not fit keeps the compact two-table form; XNTT_COMPACT_TABLES forces that everywhere. */
   uint32_t twist_table_max_mb;
   uint32_t reserved_;

@@ -15,6 +15,7 @@ int get_device(int* dev);
 int set_device(int dev);
 int dev_malloc(void** p, size_t bytes);   // returns 2 for out-of-memory, 1 for other errors
 int dev_free(void* p);
+int mem_info(size_t* free_bytes, size_t* total_bytes);  // of the current device
 int host_malloc_pinned(void** p, size_t bytes);
 int host_free_pinned(void* p);
 int memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);

@@ -173,6 +173,10 @@ int dev_free(void* p) {
   if (p) CU(cudaFree(p));
   return 0;
 }
+int mem_info(size_t* free_bytes, size_t* total_bytes) {
+  CU(cudaMemGetInfo(free_bytes, total_bytes));
+  return 0;
+}
 int host_malloc_pinned(void** p, size_t bytes) {
   CU(cudaMallocHost(p, bytes ? bytes : 16));
   return 0;
@@ -287,6 +291,11 @@ int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& pr
       e = inverse ? launch_inv_col(logn, prm, grid, st) : launch_fwd_col(logn, prm, grid, st);
     else
       e = inverse ? launch_inv_row(logn, prm, grid, st) : launch_fwd_row(logn, prm, grid, st);
+  } else if (prm.field.p == kPGold) {
+    if (col)
+      e = inverse ? launch_inv_col_gold(logn, prm, grid, st) : launch_fwd_col_gold(logn, prm, grid, st);
+    else
+      e = inverse ? launch_inv_row_gold(logn, prm, grid, st) : launch_fwd_row_gold(logn, prm, grid, st);
   } else if (prm.field.kind == kFieldShoup) {
     if (col)
       e = inverse ? launch_inv_col_sh(logn, prm, grid, st) : launch_fwd_col_sh(logn, prm, grid, st);

@@ -32,6 +32,11 @@ cudaError_t launch_fwd_row_rt(int logn, const PassParams& prm, unsigned grid, cu
 cudaError_t launch_inv_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+// Goldilocks with the modulus baked in (plain addressing only; sharded plans take the runtime-modulus kernels)
+cudaError_t launch_fwd_row_gold(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_row_gold(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_col_gold(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_col_gold(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 // runtime moduli below 2^62 with Shoup / FixedPoint64 arithmetic (field.cuh: FieldShoup)
 cudaError_t launch_fwd_row_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_row_sh(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);

@@ -337,6 +337,7 @@ struct FieldShoup : FieldOps<RuntimeModulus> {
 
 // The production prime of the reference README (README.md:19), C = 0x3917fffffff.
 typedef Field<kP0> F0;
+typedef Field<kPGold> FGold;
 
 template <class F>
 __host__ __device__ __forceinline__ F make_field(const FieldConsts& k) {

@@ -35,6 +35,9 @@ constexpr int tile_c(int logn) { return (!XNTT_FORCE_C1 && tile_logw(logn) >= 1)
 
 // The production prime of the reference README (README.md:19): 2^64 - 1827*2^31 + 1.
 constexpr u64 kP0 = 0xfffffc6e80000001ULL;
+// Goldilocks, 2^64 - 2^32 + 1: the other 64-bit modulus of the reference's tests (tests/test-ntt-reference.cpp:17-23,
+// tests/test-modulus.cpp, examples/magic-series/test-magic-series.cpp:22-39) - also gets kernels with the modulus baked in
+constexpr u64 kPGold = 0xffffffff00000001ULL;
 
 // Generalised addressing of the transform index k (used by the passes next to the all-to-all of a
 // sharded plan, where the exchange leaves / expects the data tiled): k is cut into three bit fields

@@ -565,9 +565,18 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   // forward.  The matrices of the last column pass are applied by the row pass next to it (row_applies_twist); an
   // outer column pass of a three-pass plan consumes its own, on load in the inverse and at the end of its tiles in
   // the forward direction - the latter only pays off while the matrix stays L2-resident (<= 64 MiB).
-  // Default budget 512 MiB per plan (both directions up to 2^24 cells); xntt_desc::twist_table_max_mb overrides;
+  // Default budget 512 MiB per plan (both directions up to 2^24 cells), plus the outermost matrix of a three-pass plan
+  // while memory is plentiful; xntt_desc::twist_table_max_mb overrides;
   // XNTT_COMPACT_TABLES and the column-sharded first pass of a sharded plan keep the compact two-table form.
   size_t full_budget = (size_t)(d->twist_table_max_mb ? d->twist_table_max_mb : 512u) << 20;
+  if (!d->twist_table_max_mb && q >= 3 && shard_count == 1) {
+    // three-pass plans (2^25 and above): the outermost pass has an m-entry matrix of its own (16 m bytes, twice the
+    // data of one transform).  The inverse applies it on load and gains 7 % (2^30: 32.0 -> 29.8 ms); by default it is
+    // stored when it takes no more than a quarter of the memory that is free right now.
+    const size_t big = sizeof(Tw) << pl->log2_m;
+    size_t free_b = 0, total_b = 0;
+    if (be::mem_info(&free_b, &total_b) == 0 && big <= free_b / 4) full_budget += big;
+  }
   if (d->flags & XNTT_COMPACT_TABLES) full_budget = 0;
   {
     int rem = pl->log2_m, before = 0;

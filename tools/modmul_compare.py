@@ -38,7 +38,9 @@ for L, batch in [(24, 1), (20, 64), (13, 2048), (26, 1)]:
     for name, kw in [("production_montgomery_static", {}),
                      ("p62_montgomery_runtime", {"modulus": 0x3A00000000000001, "generator": 3}),
                      ("p62_shoup_runtime", {"modulus": 0x3A00000000000001, "generator": 3, "fixed_point": True}),
-                     ("p50_shoup_runtime", {"modulus": 0x0003F00000000001, "generator": 11, "fixed_point": True})]:
+                     ("p50_shoup_runtime", {"modulus": 0x0003F00000000001, "generator": 11, "fixed_point": True}),
+                     ("goldilocks_montgomery_static", {"modulus": 0xFFFFFFFF00000001, "generator": 7}),
+                     ("p64_other_montgomery_runtime", {"modulus": 0xFFFFFFFF70000001, "generator": 3})]:
         plan = lib.plan(L, batch=batch, **kw)
         n = batch << L
         src = torch.randint(0, 2**49, (n,), dtype=torch.int64, device="cuda")
