@@ -99,6 +99,8 @@ struct PassParams {
 struct PowTable {
   u64 sq[32];  // root^(2^i) in Montgomery form
   u64 scale;   // Montgomery form of the extra factor (2^64 mod P for none)
+  u32 col0;    // kTwist: global index of the table's first column (a rank's column block of a sharded plan)
+  u32 reserved_;
 };
 // Kinnaes sum (kinnaes_kernel.cuh)
 constexpr int kKinnaesThreads = 256;

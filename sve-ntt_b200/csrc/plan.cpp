@@ -124,9 +124,11 @@ int choose_splits(int L, std::vector<int>& out) {
   return XNTT_OK;
 }
 
-int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, u64 root, u64 scale_plain) {
+int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, u64 root, u64 scale_plain,
+              u32 col0 = 0) {
   const u64 p = fc.p;
-  PowTable t;
+  PowTable t{};
+  t.col0 = col0;
   u64 r = root;
   for (int i = 0; i < 32; ++i) {
     t.sq[i] = h_to_mont(r, p);
@@ -142,7 +144,12 @@ int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int
 // column pass itself runs twist-free.
 // Holds for the last column pass whenever the planner stored its forward matrix (never for the column-sharded
 // first pass of a sharded plan).
+int log2u(u64 v);
+
 bool row_applies_twist(const xntt_plan* pl, size_t i, bool inverse = false) {
+  // the column-sharded first pass keeps its twiddle: its (per-rank) matrix is a column block, the row half of a
+  // sharded plan would need whole rows
+  if (pl->shard_count > 1 && i == 0) return false;
   // Inverse of a plan sharded over 4 or more GPUs: column pass i is the one that stores its output into the peers'
   // buffers and is bound by the links, not by arithmetic - the twiddle product is free there and would only lengthen
   // the row pass (2^30 over 8 GPUs: inverse 4.38 vs 4.45 ms; over 2 GPUs the row pass wins, 2^28 3.91 vs 3.97 ms).
@@ -175,7 +182,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.twist_hi = inverse ? ps.inv_hi : ps.fwd_hi;
     prm.twist_shift = (u32)ps.twist_shift;
     prm.twist_full = inverse ? ps.inv_full : ps.fwd_full;
-    prm.twist_full_shift = (u32)ps.log_inner;
+    prm.twist_full_shift = (u32)log2u(inner);  // columns per row of the stored matrix (a rank's block if sharded)
     if (row_applies_twist(pl, i, inverse)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
     prm.twist_col0 = sharded_first ? (u32)(inner * pl->shard_rank) : 0u;
     const u64 tiles = outer * prm.tiles_per_outer;
@@ -415,7 +422,7 @@ int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const
     prm.twist_hi = inverse ? ps.inv_hi : ps.fwd_hi;
     prm.twist_shift = (u32)ps.twist_shift;
     prm.twist_full = inverse ? ps.inv_full : nullptr;  // forward: compact, or none when the row pass applies it
-    prm.twist_full_shift = (u32)ps.log_inner;
+    prm.twist_full_shift = (u32)ps.log_inner - ((i == 0 && pl->shard_count > 1) ? (u32)log2u(pl->shard_count) : 0u);
     if (row_applies_twist(pl, i, inverse)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
     prm.twist_col0 = twist_col0;
     const u64 tiles = units * tiles_per_outer;
@@ -569,6 +576,13 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   // while memory is plentiful; xntt_desc::twist_table_max_mb overrides;
   // XNTT_COMPACT_TABLES and the column-sharded first pass of a sharded plan keep the compact two-table form.
   size_t full_budget = (size_t)(d->twist_table_max_mb ? d->twist_table_max_mb : 512u) << 20;
+  if (!d->twist_table_max_mb && shard_count > 1) {
+    // sharded plans: the rank's column block of the first pass's matrix (16 m / G bytes) for the inverse, which applies
+    // it on load - one modular product per residue instead of two in the pass that feeds the exchange
+    const size_t big = (sizeof(Tw) << pl->log2_m) / shard_count;
+    size_t free_b = 0, total_b = 0;
+    if (be::mem_info(&free_b, &total_b) == 0 && big <= free_b / 4) full_budget += big;
+  }
   if (!d->twist_table_max_mb && q >= 3 && shard_count == 1) {
     // three-pass plans (2^25 and above): the outermost pass has an m-entry matrix of its own (16 m bytes, twice the
     // data of one transform).  The inverse applies it on load and gains 7 % (2^30: 32.0 -> 29.8 ms); by default it is
@@ -605,9 +619,12 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
         words += nlo;
         off_ihi[i] = words;
         words += nhi;
-        const size_t cells = (size_t)1 << lm, bytes = cells * sizeof(Tw);
-        const bool eligible = lm <= 31 && !(shard_count > 1 && i == 0);  // a sharded first pass only sees its columns
-        if (eligible && pl->inv && bytes <= full_budget) {
+        // a sharded first pass only sees - and only stores - its own column block of the matrix, and only for the
+        // inverse (applied on load; the forward form would sit at the end of a link-bound pass)
+        const bool sharded_first = shard_count > 1 && i == 0;
+        const size_t cells = ((size_t)1 << lm) >> (sharded_first ? shard_log : 0), bytes = cells * sizeof(Tw);
+        const bool eligible = lm <= 31 && !sharded_first;
+        if ((eligible || sharded_first) && pl->inv && bytes <= full_budget) {
           full_budget -= bytes;
           use_ifull[i] = 1;
         }
@@ -655,16 +672,20 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
         rc = gen_table(pl->field, base + off_ihi[i], nhi, kPowers, 0, ps.twist_shift, root_big_inv, i == 0 ? finv : 1);
       // the matrices get allocations of their own: if the device cannot spare one, that pass and direction simply
       // keep the compact form
-      const u32 cells = 1u << lm;
+      const bool sharded_first = shard_count > 1 && i == 0;
+      const int log_cols = ps.log_inner - (sharded_first ? shard_log : 0);  // columns the table holds
+      const u32 cells = 1u << (ps.logn + log_cols);
+      const u32 col0 = sharded_first ? (u32)(((u64)1 << log_cols) * pl->shard_rank) : 0u;
       for (int dir = 0; dir < 2 && rc == XNTT_OK; ++dir) {
         if (!(dir ? use_ifull[i] : use_ffull[i])) continue;
         void* mem = nullptr;
         if (be::dev_malloc(&mem, (size_t)cells * sizeof(Tw)) != 0) continue;
         pl->matrices.push_back(mem);
         Tw* t = static_cast<Tw*>(mem);
-        rc = gen_table(pl->field, t, cells, kTwist, ps.logn, ps.log_inner, dir ? root_big_inv : root_big,
-                       (dir && i == 0) ? finv : 1);
-        (dir ? ps.inv_full : ps.fwd_full) = t;
+        rc = gen_table(pl->field, t, cells, kTwist, ps.logn, log_cols, dir ? root_big_inv : root_big,
+                       (dir && i == 0) ? finv : 1, col0);
+        // the kernels index the matrix by GLOBAL column: hand them the table shifted back by its first column
+        (dir ? ps.inv_full : ps.fwd_full) = t - col0;
       }
     }
   }

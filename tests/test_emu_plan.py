@@ -336,7 +336,10 @@ def test_sharded_peer_store_variants(emu, oracle, L, splits, G):
     a = oracle.fill_xorshift(m, SEED + 12, P0)
     want = oracle.ntt_forward(a, P0, G0)
     A = a.reshape(n0, n1)
-    plans = [emu.plan(L, splits=splits, shard_count=G, shard_rank=r) for r in range(G)]
+    # default: the inverse of the sharded first pass applies its rank's column block of the twiddle matrix;
+    # with compact tables (every other case here) the two-table form
+    compact = (L + G) % 2 == 1
+    plans = [emu.plan(L, splits=splits, shard_count=G, shard_rank=r, compact_tables=compact) for r in range(G)]
     blocks = [np.ascontiguousarray(A[:, r * n1 // G:(r + 1) * n1 // G]).reshape(-1) for r in range(G)]
     bufs = [np.full(m // G, 0xDEAD, np.uint64) for _ in range(G)]
     peers = [b.ctypes.data for b in bufs]
