@@ -93,6 +93,10 @@ uint32_t xntt_plan_batch(const xntt_plan* plan);
 uint32_t xntt_plan_launches(const xntt_plan* plan, int inverse);
 /* arithmetic the pass kernels of this plan run: 0 = Montgomery (PAdic64), 1 = Shoup (FixedPoint64, XNTT_MODMUL_FIXED_POINT) */
 uint32_t xntt_plan_modmul(const xntt_plan* plan);
+/* how the six-step twiddle of column pass `pass` is applied in the given direction: 0 = not a column pass, 1 = two
+ * sqrt(M)-entry tables (two modular products per residue), 2 = whole matrix, by the pass itself (one product),
+ * 3 = whole matrix, by the pass next to it while that loads / before it stores (one product; this pass is twist-free) */
+uint32_t xntt_plan_twiddle_form(const xntt_plan* plan, uint32_t pass, int inverse);
 /* fills out[0..n) with the log2 sizes of the passes, returns the pass count */
 uint32_t xntt_plan_splits(const xntt_plan* plan, uint32_t* out, uint32_t n);
 

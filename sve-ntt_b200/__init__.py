@@ -55,6 +55,7 @@ SYMBOLS = {
     "xntt_plan_batch": (C.c_uint32, [_P]),
     "xntt_plan_launches": (C.c_uint32, [_P, C.c_int]),
     "xntt_plan_modmul": (C.c_uint32, [_P]),
+    "xntt_plan_twiddle_form": (C.c_uint32, [_P, C.c_uint32, C.c_int]),
     "xntt_plan_splits": (C.c_uint32, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
     "xntt_forward": (C.c_int, [_P, _U64P, _U64P, _P]),
     "xntt_inverse": (C.c_int, [_P, _U64P, _U64P, _P]),
@@ -206,6 +207,10 @@ class Plan:
         buf = (C.c_uint32 * MAX_SPLITS)()
         n = self.L.lib.xntt_plan_splits(self.h, buf, MAX_SPLITS)
         return [int(buf[i]) for i in range(n)]
+
+    def twiddle_forms(self, inverse=False):
+        """per pass: 0 row pass, 1 compact tables, 2 whole matrix by the pass itself, 3 whole matrix by its neighbour"""
+        return [int(self.L.lib.xntt_plan_twiddle_form(self.h, i, 1 if inverse else 0)) for i in range(len(self.splits))]
 
     @property
     def modmul(self):

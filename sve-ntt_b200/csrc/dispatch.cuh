@@ -137,6 +137,13 @@ template <class F, int LOGN, bool COL, bool INV, bool MAP = false>
 cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
   const int kind = pass_kind(COL, INV, MAP, prm);
   if constexpr (COL) {
+    if (kind == kColPre) {
+      // production modulus, forward only (the planner asks for it nowhere else)
+      if constexpr (!INV && F::kStatic) {
+        if constexpr (F::P == kP0) return launch_kernel<F, LOGN, COL, INV, MAP, kColPre>(prm, grid, st);
+      }
+      return cudaErrorInvalidValue;
+    }
     if (kind == kCompactTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist>(prm, grid, st);
     if constexpr (INV || !MAP) {
       if (kind == kFullTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kFullTwist>(prm, grid, st);

@@ -32,7 +32,7 @@ __device__ __forceinline__ u64 pow_mont(const F& f, const PowTable& t, u32 e) {
 }
 
 // exponent of table entry idx
-__device__ __forceinline__ u32 table_exponent(u32 idx, int kind, int logn, int shift, u32 col0 = 0) {
+__device__ __forceinline__ u32 table_exponent(u32 idx, int kind, int logn, int shift, u32 col0 = 0, u32 row0 = 0) {
   if (kind == kFwdG) {
     // G[b] = omega_N^bitrev_{logn-1}(b)
     return logn > 1 ? (brev32(idx) >> (32 - (logn - 1))) : 0u;
@@ -44,8 +44,8 @@ __device__ __forceinline__ u32 table_exponent(u32 idx, int kind, int logn, int s
   }
   if (kind == kTwist) {
     // twist matrix entry (k, c), idx = (k << shift) + c: omega_M^(bitrev_logn(k) * (col0 + c)); the table holds 2^shift
-    // columns starting at global column col0 (the whole matrix: col0 = 0, M = 2^(logn + shift))
-    const u32 k = idx >> shift, c = idx & ((1u << shift) - 1u);
+    // columns starting at global column col0 and rows starting at row0 (the whole matrix: both 0)
+    const u32 k = row0 + (idx >> shift), c = idx & ((1u << shift) - 1u);
     return (logn ? (brev32(k) >> (32 - logn)) : 0u) * (col0 + c);
   }
   return idx << shift;
@@ -53,7 +53,7 @@ __device__ __forceinline__ u32 table_exponent(u32 idx, int kind, int logn, int s
 
 template <class F>
 __device__ __forceinline__ Tw table_entry(const F& f, u32 idx, int kind, int logn, int shift, const PowTable& t) {
-  return f.make_tw(pow_mont<F>(f, t, table_exponent(idx, kind, logn, shift, t.col0)));
+  return f.make_tw(pow_mont<F>(f, t, table_exponent(idx, kind, logn, shift, t.col0, t.row0)));
 }
 
 // PAdic64::to_montgomery (p-adic-64.hpp:19-22): a * 2^64 mod P, r2 = 2^128 mod P

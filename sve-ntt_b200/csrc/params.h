@@ -76,6 +76,9 @@ struct PassParams {
                          // log2 N) + k), applied while the rows are loaded (forward) or before they are stored
                          // (inverse); that column pass then runs without a twiddle
   u32 pre_rows_mask;
+  // forward column pass applying the matrix of the OUTER pass before it (kColPre): entry
+  // ((outer block & pre_rows_mask) << pre_shift) + (k << pre_kshift) + column
+  u32 pre_shift, pre_kshift;
   u32 twist_shift;
   u32 twist_full_shift;  // log2 of the number of columns of twist_full
   u32 twist_col0;      // column mode: global index of this buffer's first column (sharded plans)
@@ -100,7 +103,7 @@ struct PowTable {
   u64 sq[32];  // root^(2^i) in Montgomery form
   u64 scale;   // Montgomery form of the extra factor (2^64 mod P for none)
   u32 col0;    // kTwist: global index of the table's first column (a rank's column block of a sharded plan)
-  u32 reserved_;
+  u32 row0;    // kTwist: index of the table's first row (a rank's row block)
 };
 // Kinnaes sum (kinnaes_kernel.cuh)
 constexpr int kKinnaesThreads = 256;

@@ -51,13 +51,18 @@ namespace xntt {
 //                   kPointwise = the point-wise product of a polynomial multiply before storing; or both
 //   inverse rows  : kPostTwist = the mirror image: multiply by the matrix of the column pass that follows, before
 //                   storing (which also canonicalises); that column pass then runs twist-free
+//   forward columns: kColPre = multiply by the matrix of the OUTER pass before this one while loading (that pass then
+//                   runs twist-free, like the last column pass does when the row pass applies its matrix): every pass of
+//                   a three-pass plan at one modular product per residue
 enum TwistKind {
-  kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2, kPointwise = 3, kPreTwist = 4, kPrePointwise = 5, kPostTwist = 6
+  kNoTwist = 0, kCompactTwist = 1, kFullTwist = 2, kPointwise = 3, kPreTwist = 4, kPrePointwise = 5, kPostTwist = 6,
+  kColPre = 7
 };
 
 // the one place that decides (CUDA dispatcher and host emulator both call it)
 inline int pass_kind(bool col, bool inverse, bool map, const PassParams& prm) {
   if (col) {
+    if (!inverse && prm.pre_twist != nullptr) return kColPre;
     if (prm.twist_full != nullptr) return kFullTwist;
     if (prm.twist_lo != nullptr) return kCompactTwist;
     return kNoTwist;
@@ -423,6 +428,27 @@ __device__ __forceinline__ void apply_twist(const F& f, const PassParams& prm, u
   }
 }
 
+// forward column pass, stage 0 (kColPre): element (k, column col) of outer block o times the entry of the previous
+// pass's matrix that lies at the same place as the element itself: row (o & mask), column k * inner + col
+template <class F, class Cfg, int R>
+__device__ __forceinline__ void apply_col_pre(const F& f, const PassParams& prm, u64 (&x)[R][Cfg::C], int k0, int logs,
+                                              u32 o, u32 col) {
+  const Tw* q = prm.pre_twist + (((u64)(o & prm.pre_rows_mask) << prm.pre_shift) + col);
+  constexpr int CH = R < 8 ? R : 8;  // rows in flight at a time
+#pragma unroll
+  for (int r0 = 0; r0 < R; r0 += CH) {
+    Tw t[CH][Cfg::C];
+#pragma unroll
+    for (int r = 0; r < CH; ++r)
+#pragma unroll
+      for (int c = 0; c < Cfg::C; ++c) t[r][c] = ld_tw_stream(q + (((u64)(u32)(k0 + ((r0 + r) << logs)) << prm.pre_kshift) + c));
+#pragma unroll
+    for (int r = 0; r < CH; ++r)
+#pragma unroll
+      for (int c = 0; c < Cfg::C; ++c) x[r0 + r][c] = f.mont(x[r0 + r][c], t[r][c]);
+  }
+}
+
 // forward row pass, stage 0: residue k of row `row` times entry ((row & mask) << LOGN) + k of the matrix
 template <class F, class Cfg, int R>
 __device__ __forceinline__ void apply_pre_twist(const F& f, const PassParams& prm, u64 (&x)[R][Cfg::C], int k0, int logs,
@@ -572,6 +598,7 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
         gmem_load<Cfg, R>(prm, gsrc, row0, k0, LOGS, p, x);
       if constexpr (TWIST == kPreTwist || TWIST == kPrePointwise)
         apply_pre_twist<F, Cfg, R>(f, prm, x, k0, LOGS, row0 + (u32)(p * Cfg::C));
+      if constexpr (TWIST == kColPre) apply_col_pre<F, Cfg, R>(f, prm, x, k0, LOGS, row0, col0 + p * Cfg::C);
     } else {
       smem_load<Cfg, LOGS, R>(sm, k0, p, x);
     }
@@ -700,6 +727,7 @@ __device__ __forceinline__ void tile_origin(const PassParams& prm, u32 tile, u64
       sbase = dbase = (u64)o * prm.outer_stride + (u64)cb * Cfg::W;
     }
     col0 = prm.twist_col0 + cb * Cfg::W;
+    row0 = o;  // column mode: the outer block (kColPre indexes the previous pass's matrix with it)
   } else {
     row0 = tile << Cfg::LOGW;
     if constexpr (Cfg::MAP) {

@@ -43,6 +43,9 @@ struct PassDesc {
   // whole twiddle matrix [N][inner] (one Montgomery product per residue instead of two), when it fits the budget
   const Tw* fwd_full = nullptr;
   const Tw* inv_full = nullptr;
+  // forward matrix of an outer pass that the NEXT column pass applies while loading (kColPre); this pass then runs
+  // twist-free.  For the column-sharded first pass of a sharded plan the table is the rank's ROW block.
+  bool fwd_by_next = false;
 };
 
 struct xntt_plan {
@@ -125,10 +128,11 @@ int choose_splits(int L, std::vector<int>& out) {
 }
 
 int gen_table(const FieldConsts& fc, Tw* out, u32 count, int kind, int logn, int shift, u64 root, u64 scale_plain,
-              u32 col0 = 0) {
+              u32 col0 = 0, u32 row0 = 0) {
   const u64 p = fc.p;
   PowTable t{};
   t.col0 = col0;
+  t.row0 = row0;
   u64 r = root;
   for (int i = 0; i < 32; ++i) {
     t.sq[i] = h_to_mont(r, p);
@@ -155,6 +159,22 @@ bool row_applies_twist(const xntt_plan* pl, size_t i, bool inverse = false) {
   // the row pass (2^30 over 8 GPUs: inverse 4.38 vs 4.45 ms; over 2 GPUs the row pass wins, 2^28 3.91 vs 3.97 ms).
   if (inverse && pl->shard_count >= 4) return false;
   return i + 2 == pl->passes.size() && (inverse ? pl->passes[i].inv_full : pl->passes[i].fwd_full) != nullptr;
+}
+
+// Forward column pass i of a plan whose outer passes hand their twiddle matrix to the next pass (PassDesc::fwd_by_next):
+// the outer pass runs twist-free, the pass behind it multiplies by that matrix while loading (kColPre).
+void set_forward_handover(const xntt_plan* pl, size_t i, PassParams& prm) {
+  const PassDesc& ps = pl->passes[i];
+  if (ps.fwd_by_next) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
+  if (i > 0 && pl->passes[i - 1].fwd_by_next) {
+    const PassDesc& pp = pl->passes[i - 1];
+    prm.pre_twist = pp.fwd_full;
+    // rows of the stored table: all of them, or the rank's row block behind the exchange of a sharded plan
+    const u32 rows = (1u << pp.logn) / ((i - 1 == 0 && pl->shard_count > 1) ? pl->shard_count : 1u);
+    prm.pre_rows_mask = rows - 1u;
+    prm.pre_shift = (u32)pp.log_inner;
+    prm.pre_kshift = (u32)ps.log_inner;
+  }
 }
 
 // One pass.  `count_override` (when non-zero) replaces the number of outer blocks / rows: the row
@@ -184,6 +204,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.twist_full = inverse ? ps.inv_full : ps.fwd_full;
     prm.twist_full_shift = (u32)log2u(inner);  // columns per row of the stored matrix (a rank's block if sharded)
     if (row_applies_twist(pl, i, inverse)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
+    if (!inverse) set_forward_handover(pl, i, prm);
     prm.twist_col0 = sharded_first ? (u32)(inner * pl->shard_rank) : 0u;
     const u64 tiles = outer * prm.tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -424,6 +445,7 @@ int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const
     prm.twist_full = inverse ? ps.inv_full : nullptr;  // forward: compact, or none when the row pass applies it
     prm.twist_full_shift = (u32)ps.log_inner - ((i == 0 && pl->shard_count > 1) ? (u32)log2u(pl->shard_count) : 0u);
     if (row_applies_twist(pl, i, inverse)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
+    if (!inverse) set_forward_handover(pl, i, prm);
     prm.twist_col0 = twist_col0;
     const u64 tiles = units * tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -579,7 +601,7 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   if (!d->twist_table_max_mb && shard_count > 1) {
     // sharded plans: the rank's column block of the first pass's matrix (16 m / G bytes) for the inverse, which applies
     // it on load - one modular product per residue instead of two in the pass that feeds the exchange
-    const size_t big = (sizeof(Tw) << pl->log2_m) / shard_count;
+    const size_t big = (sizeof(Tw) << pl->log2_m) / shard_count * (q >= 3 && p == kP0 ? 2 : 1);  // + forward (kColPre)
     size_t free_b = 0, total_b = 0;
     if (be::mem_info(&free_b, &total_b) == 0 && big <= free_b / 4) full_budget += big;
   }
@@ -587,7 +609,8 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
     // three-pass plans (2^25 and above): the outermost pass has an m-entry matrix of its own (16 m bytes, twice the
     // data of one transform).  The inverse applies it on load and gains 7 % (2^30: 32.0 -> 29.8 ms); by default it is
     // stored when it takes no more than a quarter of the memory that is free right now.
-    const size_t big = sizeof(Tw) << pl->log2_m;
+    // (the forward hands its copy to the next pass, kColPre: production modulus only)
+    const size_t big = (sizeof(Tw) << pl->log2_m) * (p == kP0 ? 2 : 1);
     size_t free_b = 0, total_b = 0;
     if (be::mem_info(&free_b, &total_b) == 0 && big <= free_b / 4) full_budget += big;
   }
@@ -619,20 +642,43 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
         words += nlo;
         off_ihi[i] = words;
         words += nhi;
-        // a sharded first pass only sees - and only stores - its own column block of the matrix, and only for the
-        // inverse (applied on load; the forward form would sit at the end of a link-bound pass)
-        const bool sharded_first = shard_count > 1 && i == 0;
-        const size_t cells = ((size_t)1 << lm) >> (sharded_first ? shard_log : 0), bytes = cells * sizeof(Tw);
-        const bool eligible = lm <= 31 && !sharded_first;
-        if ((eligible || sharded_first) && pl->inv && bytes <= full_budget) {
-          full_budget -= bytes;
-          use_ifull[i] = 1;
-        }
-        // forward: the last column pass (any plan), or an outer pass of an unsharded plan while it stays in L2
-        if (eligible && pl->fwd && bytes <= full_budget && (i + 2 == q || (shard_count == 1 && bytes <= ((size_t)64 << 20)))) {
-          full_budget -= bytes;
-          use_ffull[i] = 1;
-        }
+      }
+    }
+    // Which matrices get stored.  First the last column pass (both directions: the row pass next to it applies them),
+    // then the outer passes from the outermost in: inverse = applied by the pass itself on load (a column-sharded
+    // first pass stores its rank's column block); forward = applied by the pass itself at the end of its tiles while
+    // the matrix stays L2-resident (<= 64 MiB), else handed to the NEXT column pass (production modulus; that pass has
+    // to be twist-free itself, i.e. the last column pass with its own matrix stored; a sharded first pass stores its
+    // rank's row block, which is what the pass behind the exchange sees).
+    auto cells_of = [&](size_t i, bool block) {
+      const int lm = pl->passes[i].logn + pl->passes[i].log_inner;
+      return ((size_t)1 << lm) >> (block ? shard_log : 0);
+    };
+    if (q >= 2) {
+      const size_t i = q - 2;
+      const bool sharded_first = shard_count > 1 && i == 0;
+      const int lm = pl->passes[i].logn + pl->passes[i].log_inner;
+      if (lm <= 31) {
+        const size_t bytes = cells_of(i, sharded_first) * sizeof(Tw);
+        if (pl->inv && bytes <= full_budget) full_budget -= bytes, use_ifull[i] = 1;
+        if (!sharded_first && pl->fwd && bytes <= full_budget) full_budget -= bytes, use_ffull[i] = 1;
+      }
+    }
+    for (size_t i = 0; i + 2 < q; ++i) {
+      PassDesc& ps = pl->passes[i];
+      const bool sharded_first = shard_count > 1 && i == 0;
+      const int lm = ps.logn + ps.log_inner;
+      if (lm > 31) continue;
+      const size_t bytes = cells_of(i, sharded_first) * sizeof(Tw);
+      if (pl->inv && bytes <= full_budget) full_budget -= bytes, use_ifull[i] = 1;
+      if (!pl->fwd || bytes > full_budget) continue;
+      if (!sharded_first && bytes <= ((size_t)64 << 20)) {
+        full_budget -= bytes, use_ffull[i] = 1;
+      } else if (p == kP0 && i + 3 == q && use_ffull[i + 1] && pl->passes[i + 1].logn >= 8) {
+        // (measured: with a pass of 2^7 behind it the handover loses - that pass is short enough to feel the second
+        // 16 B/residue stream: 2^26 forward 1.80 -> 1.96 ms - from 2^8 on it wins: 2^28 7.42 -> 7.13, 2^30 30.8 -> 29.8 ms)
+        full_budget -= bytes, use_ffull[i] = 1;
+        ps.fwd_by_next = true;
       }
     }
   }
@@ -673,17 +719,24 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
       // the matrices get allocations of their own: if the device cannot spare one, that pass and direction simply
       // keep the compact form
       const bool sharded_first = shard_count > 1 && i == 0;
-      const int log_cols = ps.log_inner - (sharded_first ? shard_log : 0);  // columns the table holds
-      const u32 cells = 1u << (ps.logn + log_cols);
-      const u32 col0 = sharded_first ? (u32)(((u64)1 << log_cols) * pl->shard_rank) : 0u;
       for (int dir = 0; dir < 2 && rc == XNTT_OK; ++dir) {
         if (!(dir ? use_ifull[i] : use_ffull[i])) continue;
+        // whole matrix; for a column-sharded first pass the rank's column block (inverse: this pass applies it) or its
+        // row block (forward: the pass behind the exchange applies it)
+        const bool row_block = sharded_first && !dir;
+        const int log_cols = ps.log_inner - ((sharded_first && dir) ? shard_log : 0);
+        const u32 cells = (1u << (ps.logn + ps.log_inner)) >> (sharded_first ? shard_log : 0);
+        const u32 col0 = (sharded_first && dir) ? (u32)(((u64)1 << log_cols) * pl->shard_rank) : 0u;
+        const u32 row0 = row_block ? (u32)(((1u << ps.logn) / shard_count) * pl->shard_rank) : 0u;
         void* mem = nullptr;
-        if (be::dev_malloc(&mem, (size_t)cells * sizeof(Tw)) != 0) continue;
+        if (be::dev_malloc(&mem, (size_t)cells * sizeof(Tw)) != 0) {
+          if (!dir) ps.fwd_by_next = false;  // no room: this pass keeps the compact form
+          continue;
+        }
         pl->matrices.push_back(mem);
         Tw* t = static_cast<Tw*>(mem);
         rc = gen_table(pl->field, t, cells, kTwist, ps.logn, log_cols, dir ? root_big_inv : root_big,
-                       (dir && i == 0) ? finv : 1, col0);
+                       (dir && i == 0) ? finv : 1, col0, row0);
         // the kernels index the matrix by GLOBAL column: hand them the table shifted back by its first column
         (dir ? ps.inv_full : ps.fwd_full) = t - col0;
       }
@@ -722,6 +775,13 @@ uint64_t xntt_plan_m(const xntt_plan* pl) { return pl ? (1ull << pl->log2_m) : 0
 uint32_t xntt_plan_batch(const xntt_plan* pl) { return pl ? pl->batch : 0; }
 uint32_t xntt_plan_launches(const xntt_plan* pl, int) { return pl ? (uint32_t)pl->passes.size() : 0; }
 uint32_t xntt_plan_modmul(const xntt_plan* pl) { return pl ? pl->field.kind : 0; }
+uint32_t xntt_plan_twiddle_form(const xntt_plan* pl, uint32_t pass, int inverse) {
+  if (!pl || pass >= pl->passes.size() || !pl->passes[pass].col) return 0;
+  const PassDesc& ps = pl->passes[pass];
+  if (row_applies_twist(pl, pass, inverse != 0)) return 3;
+  if (!inverse && ps.fwd_by_next) return 3;
+  return (inverse ? ps.inv_full : ps.fwd_full) != nullptr ? 2 : 1;
+}
 uint32_t xntt_plan_splits(const xntt_plan* pl, uint32_t* out, uint32_t n) {
   if (!pl) return 0;
   for (uint32_t i = 0; out && i < n && i < pl->passes.size(); ++i) out[i] = (uint32_t)pl->passes[i].logn;

@@ -123,6 +123,7 @@ static int emu_launch2(const PassParams& prm, unsigned grid) {
       case kPreTwist: emu_stages<F, Cfg, INV, kPreTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
       case kPrePointwise: emu_stages<F, Cfg, INV, kPrePointwise>(prm, sm.data(), gs, gd, col0, row0, seq); break;
       case kPostTwist: emu_stages<F, Cfg, INV, kPostTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
+      case kColPre: emu_stages<F, Cfg, INV, kColPre>(prm, sm.data(), gs, gd, col0, row0, seq); break;
       default: emu_stages<F, Cfg, INV, kNoTwist>(prm, sm.data(), gs, gd, col0, row0, seq); break;
     }
   }

@@ -326,6 +326,8 @@ def test_sharded_tiled_variants(emu, oracle, L, splits, G, K):
     (15, [3, 12], 8), (13, [1, 12], 2), (14, [2, 6, 6], 4),
     # inverse: one inner run of pass 1 per peer (block == n1b)
     (14, [4, 2, 8], 4), (16, [4, 4, 8], 4),
+    # a 2^8 pass behind the exchange: the sharded first pass hands it its forward twiddle matrix (kColPre, row block)
+    (18, [5, 8, 5], 4), (17, [3, 8, 6], 2),
 ])
 def test_sharded_peer_store_variants(emu, oracle, L, splits, G):
     """Fused exchange: the pass next to the all-to-all stores straight into every rank's buffer
@@ -338,8 +340,11 @@ def test_sharded_peer_store_variants(emu, oracle, L, splits, G):
     A = a.reshape(n0, n1)
     # default: the inverse of the sharded first pass applies its rank's column block of the twiddle matrix;
     # with compact tables (every other case here) the two-table form
-    compact = (L + G) % 2 == 1
+    compact = (L + G) % 2 == 1 and splits[1:2] != [8]
     plans = [emu.plan(L, splits=splits, shard_count=G, shard_rank=r, compact_tables=compact) for r in range(G)]
+    if len(splits) == 3 and splits[1] == 8:
+        assert plans[0].twiddle_forms(False) == [3, 3, 0]
+        assert plans[0].twiddle_forms(True) == [2, 3 if G < 4 else 2, 0]  # G >= 4: the link-bound pass keeps its own
     blocks = [np.ascontiguousarray(A[:, r * n1 // G:(r + 1) * n1 // G]).reshape(-1) for r in range(G)]
     bufs = [np.full(m // G, 0xDEAD, np.uint64) for _ in range(G)]
     peers = [b.ctypes.data for b in bufs]

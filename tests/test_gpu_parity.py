@@ -306,6 +306,14 @@ def test_three_pass_full_compare_2p26(cuda_lib, oracle):
     plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
     assert torch.equal(dst, src)
     plan.close()
+    # 2^6 x 2^8 x 2^12: here the outer pass hands its forward twiddle matrix to the 2^8 pass behind it (kColPre)
+    plan = cuda_lib.plan(L, splits=[6, 8, 12])
+    assert plan.twiddle_forms(False) == [3, 3, 0] and plan.twiddle_forms(True) == [2, 3, 0]
+    plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+    assert np.array_equal(host(dst), want)
+    plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
+    assert torch.equal(dst, src)
+    plan.close()
 
 
 @pytest.mark.parametrize("L", [28, 30])
