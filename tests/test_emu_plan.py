@@ -327,7 +327,7 @@ def test_sharded_tiled_variants(emu, oracle, L, splits, G, K):
     # inverse: one inner run of pass 1 per peer (block == n1b)
     (14, [4, 2, 8], 4), (16, [4, 4, 8], 4),
     # a 2^8 pass behind the exchange: the sharded first pass hands it its forward twiddle matrix (kColPre, row block)
-    (18, [5, 8, 5], 4), (17, [3, 8, 6], 2),
+    (18, [5, 8, 5], 2), (17, [3, 8, 6], 2),
 ])
 def test_sharded_peer_store_variants(emu, oracle, L, splits, G):
     """Fused exchange: the pass next to the all-to-all stores straight into every rank's buffer
