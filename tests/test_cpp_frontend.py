@@ -61,3 +61,14 @@ def test_magic_series_example_on_gpu():
     exe = _build("magic_series_tests_gpu")
     out = subprocess.run([exe, "--all"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ALL OK" in out.stdout and out.stdout.count(" ok") == 41, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_bench_harness_on_gpu():
+    """tests/bench-ntt.cpp re-hosted for timing (tests/cpp/bench_ntt.cpp): 'Forward, <name>' / 'Inverse, <name>' lines with
+    device-resident and host-buffer figures; here only that it runs and reports sane numbers."""
+    exe = _build("bench_ntt")
+    out = subprocess.run([exe, "--reps", "5", "--devices", "0,0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith(("Forward,", "Inverse,"))]
+    assert len(lines) == 6 and sum("multi-GPU" in ln for ln in lines) == 2, out.stdout
