@@ -675,10 +675,10 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
       if (!sharded_first && bytes <= ((size_t)64 << 20)) {
         full_budget -= bytes, use_ffull[i] = 1;
       } else if (p == kP0 && i + 3 == q && use_ffull[i + 1] && pl->passes[i + 1].logn >= 8 &&
-                 !(sharded_first && shard_count >= 4)) {
-        // (sharded over 4 or more GPUs the first pass is bound by the links, its twiddle products are free there and
-        // the pass behind the exchange would only get longer: 2^30 over 8 GPUs forward 4.06 -> 4.23 ms; over 2 GPUs
-        // the handover wins, 16.04 -> 15.50 ms)
+                 !(sharded_first && shard_count > 4)) {
+        // (sharded over 8 GPUs the first pass is bound by the links, its twiddle products are free there and the pass
+        // behind the exchange would only get longer: 2^30 forward 4.07 -> 4.23 ms; over 2 and 4 GPUs the handover wins,
+        // 16.04 -> 15.50 ms and 8.05 -> 7.96 ms)
         // (measured: with a pass of 2^7 behind it the handover loses - that pass is short enough to feel the second
         // 16 B/residue stream: 2^26 forward 1.80 -> 1.96 ms - from 2^8 on it wins: 2^28 7.42 -> 7.13, 2^30 30.8 -> 29.8 ms)
         full_budget -= bytes, use_ffull[i] = 1;
