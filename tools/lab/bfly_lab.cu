@@ -8,6 +8,7 @@
 
 #include "field.cuh"
 #include "field2.cuh"
+#include "field3.cuh"
 
 using namespace xntt;
 
@@ -42,6 +43,22 @@ __device__ __forceinline__ void bfly(u64& x0, u64& x1, u64 w, u64 wp) {
     lab::bf_v12(x0, x1, w, wp);
   } else if constexpr (V == 13) {
     lab::bf_v13(x0, x1, w, wp);
+  } else if constexpr (V == 15) {
+    lab::bf_fp64<0, 0, false>(x0, x1, w, wp);
+  } else if constexpr (V == 16) {
+    lab::bf_fp64<0, 1, false>(x0, x1, w, wp);
+  } else if constexpr (V == 17) {
+    lab::bf_fp64<0, 3, false>(x0, x1, w, wp);
+  } else if constexpr (V == 18) {
+    lab::bf_fp64<0, 0, true>(x0, x1, w, wp);
+  } else if constexpr (V == 19) {
+    lab::bf_fp64<1, 0, false>(x0, x1, w, wp);
+  } else if constexpr (V == 20) {
+    lab::bf_fp64<2, 0, false>(x0, x1, w, wp);
+  } else if constexpr (V == 21) {
+    lab::bf_fp64<0, 1, true>(x0, x1, w, wp);
+  } else if constexpr (V == 22) {
+    lab::bf_fp64<1, 1, false>(x0, x1, w, wp);
   }
 }
 
@@ -243,6 +260,14 @@ int main(int argc, char** argv) {
   if (only < 0 || only == 13) rc |= run<13, 2>("v13_lhi_from_qP_q1P0_shifts", iters);
   if (only < 0 || only == 10) rc |= run<10, 2>("v10_fix_alu_sum", iters);
   if (only < 0 || only == 11) rc |= run<11, 2>("v11_fix_alu_both", iters);
+  if (only < 0 || only == 15) rc |= run<15, 2>("v15_h2_fp64_denormal", iters);
+  if (only < 0 || only == 16) rc |= run<16, 2>("v16_h2_fp64_fix_alu_sum", iters);
+  if (only < 0 || only == 17) rc |= run<17, 2>("v17_h2_fp64_fix_alu_both", iters);
+  if (only < 0 || only == 18) rc |= run<18, 2>("v18_h2_and_q_fp64", iters);
+  if (only < 0 || only == 21) rc |= run<21, 2>("v21_h2_and_q_fp64_fix_alu_sum", iters);
+  if (only < 0 || only == 19) rc |= run<19, 2>("v19_h2_fp64_magic", iters);
+  if (only < 0 || only == 22) rc |= run<22, 2>("v22_h2_fp64_magic_fix_alu_sum", iters);
+  if (only < 0 || only == 20) rc |= run<20, 2>("v20_h2_int_2wide", iters);
   if (only < 0 || only == 6) rc |= run<6, 2>("v6_probe_nofix", iters, false);
   if (only < 0 || only == 7) rc |= run<7, 2>("v7_probe_mont_only", iters, false);
   return rc;
