@@ -72,3 +72,52 @@ def test_bench_harness_on_gpu():
     assert out.returncode == 0, out.stdout + out.stderr
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith(("Forward,", "Inverse,"))]
     assert len(lines) == 6 and sum("multi-GPU" in ln for ln in lines) == 2, out.stdout
+
+
+# --- the reference's OWN test sources, unmodified --------------------------------------------------------------------
+# tests/bench-ntt.cpp (driver: random input, NTT<kernel>::compute_forward / compute_inverse, every word against
+# NTTReference, bench-ntt.cpp:60-64) with each tests/ntt-tests/*.hpp as NTT_TEST_CASE_FILE, and tests/test-modulus.cpp,
+# compiled from /root/reference where they lie against the drop-in headers by `make -C oracle refbench` (outputs in
+# oracle/_ref/refbench/, which travels to the GPU box like the other oracle/_ref files).  Only tests/cpp/shim stands in for
+# Google Benchmark / GoogleTest and for the SVE intrinsics of the reference's tests/utility.hpp.
+REFBENCH = os.path.join(ROOT, "oracle", "_ref", "refbench")
+REFERENCE = "/root/reference"
+REF_CASES = 15  # tests/ntt-tests/*.hpp: 10 scalar + 5 SVE compositions
+
+
+def _refbench(suffix):
+    if os.path.isdir(os.path.join(REFERENCE, "tests", "ntt-tests")):
+        subprocess.run(["make", "-j", str(os.cpu_count() or 4), "refbench"], cwd=os.path.join(ROOT, "oracle"), check=True,
+                       stdout=subprocess.DEVNULL)
+    exes = sorted(os.path.join(REFBENCH, f) for f in (os.listdir(REFBENCH) if os.path.isdir(REFBENCH) else [])
+                  if f.endswith(suffix))
+    if not exes:
+        pytest.skip("oracle/_ref/refbench not built (needs the reference checkout at build time)")
+    return exes
+
+
+def _run_reference_driver(exes):
+    assert len(exes) == REF_CASES, exes
+    for exe in exes:
+        out = subprocess.run([exe, "--iterations=2"], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, (exe, out.stdout + out.stderr)
+        lines = [ln for ln in out.stdout.splitlines() if ln.endswith(": ok")]
+        assert len(lines) == 2 and lines[0].startswith("Forward, ") and lines[1].startswith("Inverse, "), (exe, out.stdout)
+
+
+def test_unmodified_reference_driver_on_emulator():
+    _run_reference_driver(_refbench(".emu"))
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_driver_on_gpu():
+    _run_reference_driver(_refbench(".gpu"))
+
+
+def test_unmodified_reference_test_modulus():
+    """tests/test-modulus.cpp (sums of all order-th roots vanish, 7 orders up to 2^28, Goldilocks) against the drop-in
+    sventt::Modulus."""
+    _refbench(".emu")
+    exe = os.path.join(REFBENCH, "test-modulus")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "1 test(s), 0 failure(s)" in out.stdout, out.stdout[-2000:] + out.stderr
