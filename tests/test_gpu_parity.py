@@ -586,6 +586,47 @@ def test_fused_forward_multiply(cuda_lib, oracle, L, splits, N, g):
     plan.close()
 
 
+@pytest.mark.parametrize("L,batch", [(17, 1), (20, 3), (26, 1)])
+def test_device_calls_capture_into_a_cuda_graph(cuda_lib, oracle, L, batch):
+    """The device entry points only enqueue kernels on the caller's stream (no allocation, no synchronisation), so a
+    forward + inverse pair can be captured into a CUDA graph and replayed: two- and three-pass plans, replayed on fresh
+    data, bit-exact against the oracle."""
+    import torch
+    m = 1 << L
+    plan = cuda_lib.plan(L, batch=batch)
+    a = oracle.fill_xorshift(m * batch, SEED + 7 * L, P0)
+    src, spec, back = dev(a), torch.empty(m * batch, dtype=torch.int64, device="cuda"), \
+        torch.empty(m * batch, dtype=torch.int64, device="cuda")
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        # first launches set kernel attributes: keep them out of the capture
+        plan.forward(spec.data_ptr(), src.data_ptr(), side.cuda_stream)
+        plan.inverse(back.data_ptr(), spec.data_ptr(), side.cuda_stream)
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        st = torch.cuda.current_stream().cuda_stream
+        plan.forward(spec.data_ptr(), src.data_ptr(), st)
+        plan.inverse(back.data_ptr(), spec.data_ptr(), st)
+    for rep in range(2):
+        b = oracle.fill_xorshift(m * batch, SEED + 11 * L + rep, P0)
+        src.copy_(dev(b))
+        spec.fill_(0x5555555555555555)
+        back.fill_(0x2AAAAAAAAAAAAAAA)
+        graph.replay()
+        torch.cuda.synchronize()
+        got = host(spec)
+        if L <= 20:
+            for i in range(batch):
+                assert np.array_equal(got[i * m:(i + 1) * m], oracle.ntt_forward(b[i * m:(i + 1) * m].copy(), P0, G0)), (L, i, rep)
+        else:
+            # 2^26: directly evaluated output words
+            for pos in (0, 1, 12345, m - 1):
+                assert int(got[pos]) == oracle.dft_point(b, P0, G0, pos), (L, pos, rep)
+        assert np.array_equal(host(back), b), (L, rep)
+    plan.close()
+
+
 def test_transpose_contract(cuda_lib):
     """tests/bench-transpose.cpp: every shape transposed and transposed back must return the input;
     sizes 2^8..2^13, pads {0, 32}, plus ragged shapes and the in-place square form."""
