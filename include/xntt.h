@@ -49,7 +49,15 @@ enum {
    * alternative modmul type FixedPoint64SVE (include/sventt/modmul/sve/fixed-point-64.hpp:13-69).  Same results; legal
    * for moduli below 2^62 (lazy values in [0, 4p)), where it needs 6 instead of 10 wide multiplies per butterfly.  Ignored
    * (Montgomery kernels run) for larger moduli and for the production modulus, whose kernels have it baked in. */
-  XNTT_MODMUL_FIXED_POINT = 8
+  XNTT_MODMUL_FIXED_POINT = 8,
+  /* Tile shape of the passes.  A pass normally works on tiles of 2^13 residues (64 KiB of shared memory per CTA).  Plans
+   * of at most 2^20 residues (m * batch) would leave most SMs without a tile, so their passes run on narrow tiles - a
+   * quarter of the residues, four times the CTAs - where the pass length has one (rows up to 2^11, columns up to 2^9;
+   * production modulus and runtime Montgomery kernels, unsharded plans), and the planner's own decomposition of such a
+   * plan keeps its passes that short.  Same results either way.  These two flags override the size rule (tests,
+   * measurements): never narrow / narrow wherever a pass has the variant. */
+  XNTT_TILES_WIDE = 16,
+  XNTT_TILES_NARROW = 32
 };
 
 #define XNTT_MAX_SPLITS 4
@@ -64,7 +72,7 @@ typedef struct xntt_desc {
   uint32_t batch;          /* number of back-to-back transforms in one buffer (0 means 1)           */
   uint64_t inverse_factor; /* inverse output is divided by this (0 or 1: unscaled); the reference's */
                            /* inverse_factor layer argument (layer/sve/radix-eight.hpp:19)          */
-  uint32_t flags;          /* XNTT_ENABLE_* (neither bit = both, wrapper.hpp:34-35) | XNTT_COMPACT_TABLES | XNTT_MODMUL_FIXED_POINT */
+  uint32_t flags;          /* XNTT_ENABLE_* (neither bit = both, wrapper.hpp:34-35) | XNTT_COMPACT_TABLES | XNTT_MODMUL_FIXED_POINT | XNTT_TILES_* */
   int32_t device;          /* CUDA device ordinal, -1 = current                                     */
   uint32_t n_splits;       /* 0 = let the planner decompose m; else the six-step decomposition      */
   uint32_t split_log2[XNTT_MAX_SPLITS]; /* m = prod 2^split_log2[i], outermost (column) first       */
@@ -97,6 +105,9 @@ uint32_t xntt_plan_modmul(const xntt_plan* plan);
  * sqrt(M)-entry tables (two modular products per residue), 2 = whole matrix, by the pass itself (one product),
  * 3 = whole matrix, by the pass next to it while that loads / before it stores (one product; this pass is twist-free) */
 uint32_t xntt_plan_twiddle_form(const xntt_plan* plan, uint32_t pass, int inverse);
+/* log2 of the residues one CTA of pass `pass` works on (13 for whole tiles and less for short passes, 11 or less for
+ * narrow tiles); 0 for an invalid pass index */
+uint32_t xntt_plan_tile_log2(const xntt_plan* plan, uint32_t pass);
 /* fills out[0..n) with the log2 sizes of the passes, returns the pass count */
 uint32_t xntt_plan_splits(const xntt_plan* plan, uint32_t* out, uint32_t n);
 

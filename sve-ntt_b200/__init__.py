@@ -18,6 +18,7 @@ G0 = 3
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_ALLOC, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4, -5
 ENABLE_FORWARD, ENABLE_INVERSE, COMPACT_TABLES, MODMUL_FIXED_POINT = 1, 2, 4, 8
+TILES_WIDE, TILES_NARROW = 16, 32
 MAX_SPLITS = 4
 
 
@@ -56,6 +57,7 @@ SYMBOLS = {
     "xntt_plan_launches": (C.c_uint32, [_P, C.c_int]),
     "xntt_plan_modmul": (C.c_uint32, [_P]),
     "xntt_plan_twiddle_form": (C.c_uint32, [_P, C.c_uint32, C.c_int]),
+    "xntt_plan_tile_log2": (C.c_uint32, [_P, C.c_uint32]),
     "xntt_plan_splits": (C.c_uint32, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
     "xntt_forward": (C.c_int, [_P, _U64P, _U64P, _P]),
     "xntt_inverse": (C.c_int, [_P, _U64P, _U64P, _P]),
@@ -170,14 +172,16 @@ class Plan:
 
     def __init__(self, library, log2_m, modulus=P0, generator=G0, batch=1, inverse_factor=None,
                  forward=True, inverse=True, device=-1, splits=None, shard_count=0, shard_rank=0,
-                 compact_tables=False, twist_table_max_mb=0, fixed_point=False):
+                 compact_tables=False, twist_table_max_mb=0, fixed_point=False, tiles=None):
+        """tiles: None = the planner's size rule, "wide" / "narrow" = XNTT_TILES_WIDE / XNTT_TILES_NARROW"""
         self.L = library
         d = Desc()
         d.modulus, d.generator = modulus, generator
         d.log2_m, d.batch = log2_m, batch
         d.inverse_factor = (1 << log2_m) if inverse_factor is None else inverse_factor
         d.flags = (ENABLE_FORWARD if forward else 0) | (ENABLE_INVERSE if inverse else 0) | \
-            (COMPACT_TABLES if compact_tables else 0) | (MODMUL_FIXED_POINT if fixed_point else 0)
+            (COMPACT_TABLES if compact_tables else 0) | (MODMUL_FIXED_POINT if fixed_point else 0) | \
+            {None: 0, "wide": TILES_WIDE, "narrow": TILES_NARROW}[tiles]
         d.device = device
         if splits:
             d.n_splits = len(splits)
@@ -207,6 +211,11 @@ class Plan:
         buf = (C.c_uint32 * MAX_SPLITS)()
         n = self.L.lib.xntt_plan_splits(self.h, buf, MAX_SPLITS)
         return [int(buf[i]) for i in range(n)]
+
+    @property
+    def tile_log2(self):
+        """log2 of the residues one CTA works on, per pass"""
+        return [int(self.L.lib.xntt_plan_tile_log2(self.h, i)) for i in range(len(self.splits))]
 
     def twiddle_forms(self, inverse=False):
         """per pass: 0 row pass, 1 compact tables, 2 whole matrix by the pass itself, 3 whole matrix by its neighbour"""

@@ -269,7 +269,21 @@ const char* last_error() { return g_err.c_str(); }
 int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (map) {
+  if (prm.narrow) {
+    // narrow tiles: plain addressing, production modulus or runtime Montgomery (the planner asks for nothing else)
+    if (map || !field_has_narrow(prm.field) || !has_narrow_tile(logn, col)) return fail(cudaErrorInvalidValue);
+    if (prm.field.p == kP0) {
+      if (col)
+        e = inverse ? launch_inv_col_narrow(logn, prm, grid, st) : launch_fwd_col_narrow(logn, prm, grid, st);
+      else
+        e = inverse ? launch_inv_row_narrow(logn, prm, grid, st) : launch_fwd_row_narrow(logn, prm, grid, st);
+    } else {
+      if (col)
+        e = inverse ? launch_inv_col_narrow_rt(logn, prm, grid, st) : launch_fwd_col_narrow_rt(logn, prm, grid, st);
+      else
+        e = inverse ? launch_inv_row_narrow_rt(logn, prm, grid, st) : launch_fwd_row_narrow_rt(logn, prm, grid, st);
+    }
+  } else if (map) {
     if (prm.field.p == kP0) {
       if (col)
         e = inverse ? launch_inv_col_map(logn, prm, grid, st) : launch_fwd_col_map(logn, prm, grid, st);

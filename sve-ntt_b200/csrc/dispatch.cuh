@@ -32,6 +32,15 @@ cudaError_t launch_fwd_row_rt(int logn, const PassParams& prm, unsigned grid, cu
 cudaError_t launch_inv_row_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_fwd_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_col_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+// narrow tiles (params.h: pass_logw(logn, true)): production modulus and runtime Montgomery, plain addressing
+cudaError_t launch_fwd_row_narrow(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_row_narrow(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_col_narrow(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_col_narrow(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_row_narrow_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_row_narrow_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_fwd_col_narrow_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
+cudaError_t launch_inv_col_narrow_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 // Goldilocks with the modulus baked in (plain addressing only; sharded plans take the runtime-modulus kernels)
 cudaError_t launch_fwd_row_gold(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
 cudaError_t launch_inv_row_gold(int logn, const PassParams& prm, unsigned grid, cudaStream_t st);
@@ -92,12 +101,13 @@ cudaError_t launch_row_tma(const PassParams& prm, unsigned grid, cudaStream_t st
 }
 #endif
 
-template <class F, int LOGN, bool COL, bool INV, bool MAP, int TWIST>
+template <class F, int LOGN, bool COL, bool INV, bool MAP, int TWIST, bool NARROW = false>
 cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st) {
 #if XNTT_TMA_ROWS
   if constexpr (!COL && !MAP && LOGN == 13 && F::kStatic) return launch_row_tma<F, INV, TWIST>(prm, grid, st);
 #endif
-  constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
+  static_assert(!NARROW || (!MAP && has_narrow_tile(LOGN, COL)), "no narrow tile for this pass");
+  constexpr int LOGW = pass_logw(LOGN, NARROW), C = pass_c(LOGN, NARROW);
   typedef PassCfg<LOGN, LOGW, C, COL> Cfg;
   auto kern = pass_kernel<F, LOGN, LOGW, C, COL, INV, TWIST, MAP>;
   // function attributes live in the context of the device they were set on: once per kernel and device, and
@@ -133,34 +143,34 @@ cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st)
 // sharded plans serve the pass next to the exchange: a column pass there has the compact form, plus what the planner
 // uses for an inner column pass - the whole matrix in the inverse, none at all in the forward direction (the row pass
 // applies it) - and a row pass is always plain.
-template <class F, int LOGN, bool COL, bool INV, bool MAP = false>
+template <class F, int LOGN, bool COL, bool INV, bool MAP = false, bool NARROW = false>
 cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
   const int kind = pass_kind(COL, INV, MAP, prm);
   if constexpr (COL) {
     if (kind == kColPre) {
       // production modulus, forward only (the planner asks for it nowhere else)
       if constexpr (!INV && F::kStatic) {
-        if constexpr (F::P == kP0) return launch_kernel<F, LOGN, COL, INV, MAP, kColPre>(prm, grid, st);
+        if constexpr (F::P == kP0) return launch_kernel<F, LOGN, COL, INV, MAP, kColPre, NARROW>(prm, grid, st);
       }
       return cudaErrorInvalidValue;
     }
-    if (kind == kCompactTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist>(prm, grid, st);
+    if (kind == kCompactTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kCompactTwist, NARROW>(prm, grid, st);
     if constexpr (INV || !MAP) {
-      if (kind == kFullTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kFullTwist>(prm, grid, st);
+      if (kind == kFullTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kFullTwist, NARROW>(prm, grid, st);
     }
     // twist-free: the row pass next to it applies the matrix
-    if (kind == kNoTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
+    if (kind == kNoTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist, NARROW>(prm, grid, st);
     return cudaErrorInvalidValue;
   } else {
     if constexpr (!INV && !MAP) {
-      if (kind == kPointwise) return launch_kernel<F, LOGN, COL, INV, MAP, kPointwise>(prm, grid, st);
-      if (kind == kPreTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kPreTwist>(prm, grid, st);
-      if (kind == kPrePointwise) return launch_kernel<F, LOGN, COL, INV, MAP, kPrePointwise>(prm, grid, st);
+      if (kind == kPointwise) return launch_kernel<F, LOGN, COL, INV, MAP, kPointwise, NARROW>(prm, grid, st);
+      if (kind == kPreTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kPreTwist, NARROW>(prm, grid, st);
+      if (kind == kPrePointwise) return launch_kernel<F, LOGN, COL, INV, MAP, kPrePointwise, NARROW>(prm, grid, st);
     }
     if constexpr (INV && !MAP) {
-      if (kind == kPostTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kPostTwist>(prm, grid, st);
+      if (kind == kPostTwist) return launch_kernel<F, LOGN, COL, INV, MAP, kPostTwist, NARROW>(prm, grid, st);
     }
-    return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist>(prm, grid, st);
+    return launch_kernel<F, LOGN, COL, INV, MAP, kNoTwist, NARROW>(prm, grid, st);
   }
 }
 
@@ -170,5 +180,8 @@ cudaError_t launch_one(const PassParams& prm, unsigned grid, cudaStream_t st) {
 #define XNTT_CASE_MAP(F, L, COL, INV) \
   case L:                             \
     return launch_one<F, L, COL, INV, true>(prm, grid, st);
+#define XNTT_CASE_NARROW(F, L, COL, INV) \
+  case L:                                \
+    return launch_one<F, L, COL, INV, false, true>(prm, grid, st);
 
 }  // namespace xntt

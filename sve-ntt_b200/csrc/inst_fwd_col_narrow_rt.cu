@@ -1,0 +1,20 @@
+// SPDX-License-Identifier: Apache-2.0
+// Instantiations of pass_kernel: fwd_col, narrow tiles, field FieldRT.
+#include "dispatch.cuh"
+namespace xntt {
+cudaError_t launch_fwd_col_narrow_rt(int logn, const PassParams& prm, unsigned grid, cudaStream_t st) {
+  switch (logn) {
+    XNTT_CASE_NARROW(FieldRT, 1, true, false)
+    XNTT_CASE_NARROW(FieldRT, 2, true, false)
+    XNTT_CASE_NARROW(FieldRT, 3, true, false)
+    XNTT_CASE_NARROW(FieldRT, 4, true, false)
+    XNTT_CASE_NARROW(FieldRT, 5, true, false)
+    XNTT_CASE_NARROW(FieldRT, 6, true, false)
+    XNTT_CASE_NARROW(FieldRT, 7, true, false)
+    XNTT_CASE_NARROW(FieldRT, 8, true, false)
+    XNTT_CASE_NARROW(FieldRT, 9, true, false)
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+}  // namespace xntt

@@ -33,6 +33,15 @@ constexpr int tile_logw(int logn) {
 #endif
 constexpr int tile_c(int logn) { return (!XNTT_FORCE_C1 && tile_logw(logn) >= 1) ? 2 : 1; }
 
+// Narrow tiles: a quarter of the residues of a whole tile, i.e. four times the CTAs and a quarter of the work per
+// thread - for transforms too small to fill the GPU with whole tiles (a 2^17 transform is 16 whole tiles on 148 SMs;
+// what it costs then is the life of ONE CTA, about 2 us per butterfly level).  Column tiles stay at least four columns
+// (32 bytes) wide.
+constexpr int kNarrowShift = 2;
+constexpr bool has_narrow_tile(int logn, bool col) { return tile_logw(logn) - kNarrowShift >= (col ? 2 : 0); }
+constexpr int pass_logw(int logn, bool narrow) { return narrow ? tile_logw(logn) - kNarrowShift : tile_logw(logn); }
+constexpr int pass_c(int logn, bool narrow) { return (!XNTT_FORCE_C1 && pass_logw(logn, narrow) >= 1) ? 2 : 1; }
+
 // The production prime of the reference README (README.md:19): 2^64 - 1827*2^31 + 1.
 constexpr u64 kP0 = 0xfffffc6e80000001ULL;
 // Goldilocks, 2^64 - 2^32 + 1: the other 64-bit modulus of the reference's tests (tests/test-ntt-reference.cpp:17-23,
@@ -96,7 +105,12 @@ struct PassParams {
   u32 peer_on;
   const u64* pointwise;  // forward row pass: multiply output word i by pointwise[i] * 2^-64 (fused
                          // PAdic64::multiply_normalize against a to_montgomery'd spectrum), or null
+  u32 narrow;            // run the narrow-tile kernel of this pass length (pass_logw(logn, true); plain addressing only)
 };
+// fields whose kernels exist in the narrow-tile form: the production prime and runtime Montgomery
+inline bool field_has_narrow(const FieldConsts& fc) {
+  return fc.p == kP0 || (fc.kind == kFieldMontgomery && fc.p != kPGold);
+}
 
 // Input of the on-device table generator: out[idx] = scale * root^e(idx), Montgomery pair.
 struct PowTable {

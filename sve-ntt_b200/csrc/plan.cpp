@@ -34,6 +34,7 @@ struct PassDesc {
   int log_inner = 0;  // column mode: log2 of the distance between consecutive k (unsharded)
   int log_outer = 0;  // log2 of the number of independent [N][inner] blocks per transform
   int twist_shift = 0;
+  bool narrow = false;  // narrow tiles (params.h: pass_logw): plans too small to fill the GPU with whole tiles
   const Tw* fwd_tw = nullptr;
   const Tw* inv_tw = nullptr;
   const Tw* fwd_lo = nullptr;
@@ -102,10 +103,22 @@ struct DeviceGuard {
   }
 };
 
-int choose_splits(int L, std::vector<int>& out) {
+// Plans of at most this many residues (transform length x batch) are "small": whole tiles (2^13 residues) would leave
+// most of the 148 SMs idle - 2^20 residues are 128 whole tiles for 296 resident CTAs - so their passes run on narrow
+// tiles where a pass length has one, and the planner's own decomposition keeps both passes short enough to have one.
+// Measured on B200 (tools/small_sizes.py, one forward transform, whole -> narrow tiles): 2^16 28.5 -> 13.3 us,
+// 2^17 28.7 -> 14.4, 2^18 28.9 -> 16.4, 2^19 31.9 -> 21.5, 2^20 33.8 -> 30.8; at 2^21 whole tiles win (56 vs 60 us).
+constexpr int kSmallPlanLog = 20;
+
+int choose_splits(int L, std::vector<int>& out, bool small = false) {
   out.clear();
   if (L <= kMaxRowLog) {
     out.push_back(L);
+  } else if (small && L <= 20) {
+    // column pass of at most 2^9 (narrow column tiles stay four columns wide), row pass of at most 2^11
+    const int l0 = L / 2 < 9 ? L / 2 : 9;
+    out.push_back(l0);
+    out.push_back(L - l0);
   } else if (L <= 24) {
     int l1 = L - 8 > 12 ? 12 : L - 8;  // prefer a 2^12 row pass (four clean radix-8 stages)
     if (l1 < L / 2) l1 = L / 2;
@@ -188,7 +201,8 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
   prm.tw = inverse ? ps.inv_tw : ps.fwd_tw;
   prm.scale = pl->scale;
   prm.field = pl->field;
-  const int logw = tile_logw(ps.logn);
+  const int logw = pass_logw(ps.logn, ps.narrow);
+  prm.narrow = ps.narrow ? 1u : 0u;
   unsigned grid;
   if (ps.col) {
     const bool sharded_first = (i == 0 && pl->shard_count > 1);
@@ -294,7 +308,7 @@ int host_row_pipeline(const xntt_plan* pl, u64* d, uint64_t* dst, const uint64_t
   const size_t q = pl->passes.size(), last = q - 1;
   const PassDesc& rp = pl->passes[last];
   const u64 rows = (u64)pl->batch << (pl->log2_m - rp.logn);
-  while (chunks > 1 && (rows % chunks != 0 || (rows / chunks) % (1u << tile_logw(rp.logn)) != 0)) chunks /= 2;
+  while (chunks > 1 && (rows % chunks != 0 || (rows / chunks) % (1u << pass_logw(rp.logn, rp.narrow)) != 0)) chunks /= 2;
   const u64 per = rows / chunks;
   const size_t chunk_words = (size_t)per << rp.logn, chunk_bytes = chunk_words * sizeof(u64);
   const size_t bytes = (sizeof(u64) << pl->log2_m) * pl->batch;
@@ -501,6 +515,16 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
   // g must generate the order-m subgroup: omega^(m/2) == -1
   if (h_pow(root_m, m / 2, p) != p - 1) return XNTT_ERR_INVALID;
 
+  // narrow tiles: small unsharded plans of a field that has the kernels, unless a flag says otherwise
+  bool narrow_tiles = false;
+  {
+    FieldConsts fc{};
+    fc.p = p;
+    fc.kind = ((d->flags & XNTT_MODMUL_FIXED_POINT) && p < (1ull << 62) && p != kP0) ? kFieldShoup : kFieldMontgomery;
+    const u64 residues = (u64)(d->batch ? d->batch : 1) << d->log2_m;
+    narrow_tiles = d->shard_count <= 1 && field_has_narrow(fc) && !(d->flags & XNTT_TILES_WIDE) &&
+                   ((d->flags & XNTT_TILES_NARROW) || residues <= (1ull << kSmallPlanLog));
+  }
   std::vector<int> splits;
   if (d->n_splits) {
     if (d->n_splits > XNTT_MAX_SPLITS) return XNTT_ERR_INVALID;
@@ -512,7 +536,7 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
     // IterativeNTT / RecursiveNTT static_assert: the product of the radices equals m
     if (sum != d->log2_m) return XNTT_ERR_INVALID;
   } else {
-    const int rc = choose_splits((int)d->log2_m, splits);
+    const int rc = choose_splits((int)d->log2_m, splits, narrow_tiles);
     if (rc != XNTT_OK) return rc;
   }
   const u32 shard_count = d->shard_count ? d->shard_count : 1;
@@ -624,6 +648,7 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
       ps.col = i + 1 < q;
       ps.log_inner = rem;
       ps.log_outer = before;
+      ps.narrow = narrow_tiles && has_narrow_tile(ps.logn, ps.col);
       before += ps.logn;
       const size_t n = 1ull << ps.logn;
       off_fwd[i] = words;
@@ -785,6 +810,11 @@ uint32_t xntt_plan_twiddle_form(const xntt_plan* pl, uint32_t pass, int inverse)
   if (row_applies_twist(pl, pass, inverse != 0)) return 3;
   if (!inverse && ps.fwd_by_next) return 3;
   return (inverse ? ps.inv_full : ps.fwd_full) != nullptr ? 2 : 1;
+}
+uint32_t xntt_plan_tile_log2(const xntt_plan* pl, uint32_t pass) {
+  if (!pl || pass >= pl->passes.size()) return 0;
+  const PassDesc& ps = pl->passes[pass];
+  return (uint32_t)(ps.logn + pass_logw(ps.logn, ps.narrow));
 }
 uint32_t xntt_plan_splits(const xntt_plan* pl, uint32_t* out, uint32_t n) {
   if (!pl) return 0;

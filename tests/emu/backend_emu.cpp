@@ -100,9 +100,9 @@ static void emu_stages(const PassParams& prm, typename Slot<Cfg::C>::type* sm, c
   }
 }
 
-template <class F, int LOGN, bool COL, bool INV, bool MAP>
+template <class F, int LOGN, bool COL, bool INV, bool MAP, bool NARROW = false>
 static int emu_launch2(const PassParams& prm, unsigned grid) {
-  constexpr int LOGW = tile_logw(LOGN), C = tile_c(LOGN);
+  constexpr int LOGW = pass_logw(LOGN, NARROW), C = pass_c(LOGN, NARROW);
   typedef PassCfg<LOGN, LOGW, C, COL, MAP> Cfg;
   std::vector<typename Slot<C>::type> sm((size_t)Cfg::N * Cfg::NP + 1);
   for (unsigned tile = 0; tile < grid; ++tile) {
@@ -138,6 +138,16 @@ static int emu_launch(const PassParams& prm, unsigned grid) {
     if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV, true>(prm, grid);
     if (prm.field.kind == kFieldShoup) return emu_launch2<FieldShoup, LOGN, COL, INV, true>(prm, grid);
     return emu_launch2<FieldRT, LOGN, COL, INV, true>(prm, grid);
+  }
+  if (prm.narrow) {
+    // same rule as backend_cuda.cu: production modulus or runtime Montgomery, pass lengths with a narrow tile
+    if constexpr (has_narrow_tile(LOGN, COL)) {
+      if (field_has_narrow(prm.field)) {
+        if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV, false, true>(prm, grid);
+        return emu_launch2<FieldRT, LOGN, COL, INV, false, true>(prm, grid);
+      }
+    }
+    return 1;
   }
   if (prm.field.p == kP0) return emu_launch2<F0, LOGN, COL, INV, false>(prm, grid);
   if (prm.field.kind == kFieldShoup) return emu_launch2<FieldShoup, LOGN, COL, INV, false>(prm, grid);

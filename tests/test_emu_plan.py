@@ -51,6 +51,42 @@ def test_explicit_splits(emu, oracle, L, splits):
     assert roundtrip(emu, oracle, L, splits=splits) == splits
 
 
+@pytest.mark.parametrize("L,splits,batch", [(5, None, 3), (9, None, 1), (11, None, 5), (14, None, 1), (17, [8, 9], 1), (18, None, 1),
+                                            (20, None, 1), (16, [5, 5, 6], 2), (15, [9, 6], 1), (13, [9, 4], 3), (19, [8, 11], 1)])
+def test_tile_shapes(emu, oracle, L, splits, batch):
+    """Every pass exists on whole tiles (2^13 residues per CTA) and, up to 2^11 rows / 2^9 columns, on narrow tiles (a
+    quarter of that): XNTT_TILES_WIDE / XNTT_TILES_NARROW force either, the default picks narrow for plans of at most
+    2^20 residues.  Same words from all three."""
+    roundtrip(emu, oracle, L, splits=splits, batch=batch, tiles="wide")
+    roundtrip(emu, oracle, L, splits=splits, batch=batch, tiles="narrow")
+    roundtrip(emu, oracle, L, splits=splits, batch=batch, tiles="narrow", compact_tables=True, inverse_factor=5)
+    wide = emu.plan(L, splits=splits, batch=batch, tiles="wide")
+    narrow = emu.plan(L, splits=splits, batch=batch, tiles="narrow")
+    auto = emu.plan(L, splits=splits, batch=batch)
+    assert all(t <= 13 for t in wide.tile_log2) and all(t <= 11 or n > 11 for t, n in zip(narrow.tile_log2, narrow.splits))
+    assert any(a < b for a, b in zip(narrow.tile_log2, wide.tile_log2)) or all(n >= 12 for n in narrow.splits)
+    assert auto.tile_log2 == narrow.tile_log2  # all of these are small plans
+    if splits is None and 14 <= L <= 20:
+        assert auto.splits[0] <= 9 and auto.splits[1] <= 11  # both passes have a narrow tile
+    for pl in (wide, narrow, auto):
+        pl.close()
+
+
+def test_tile_shape_rule_for_large_plans(emu):
+    """Above 2^20 residues the planner keeps whole tiles and its large-plan decomposition."""
+    big = emu.plan(22)
+    assert big.splits == [10, 12] and big.tile_log2 == [13, 13]
+    batched = emu.plan(12, batch=1024)
+    assert batched.tile_log2 == [13]
+    small = emu.plan(10, batch=4)
+    assert small.tile_log2 == [11]
+    no_variant = emu.plan(12, batch=4)  # a 2^12 row pass has no narrow tile
+    assert no_variant.tile_log2 == [13]
+    no_variant.close()
+    for pl in (big, batched, small):
+        pl.close()
+
+
 @pytest.mark.parametrize("L,splits", [(14, None), (17, [8, 9]), (16, [5, 5, 6]), (13, [1, 12])])
 def test_compact_twiddle_tables(emu, oracle, L, splits):
     """The six-step twiddles exist in two forms (whole matrix / two sqrt(M) tables, XNTT_COMPACT_TABLES): the

@@ -586,6 +586,58 @@ def test_fused_forward_multiply(cuda_lib, oracle, L, splits, N, g):
     plan.close()
 
 
+@pytest.mark.parametrize("L,splits,batch", [(5, None, 3), (9, None, 1), (11, None, 37), (14, None, 1), (17, [8, 9], 1), (17, None, 3),
+                                            (18, None, 1), (19, None, 1), (20, None, 1), (20, None, 2), (21, None, 1),
+                                            (16, [5, 5, 6], 2), (15, [9, 6], 1), (13, [9, 4], 3), (19, [8, 11], 1)])
+def test_tile_shapes(cuda_lib, oracle, L, splits, batch):
+    """Whole tiles (2^13 residues per CTA) against narrow tiles (a quarter: plans of at most 2^20 residues take them by
+    default, XNTT_TILES_WIDE / XNTT_TILES_NARROW force either): both against the oracle, forward and inverse, with both
+    twiddle forms."""
+    import torch
+    m = 1 << L
+    a = oracle.fill_xorshift(m * batch, SEED + 3 * L, P0)
+    want = np.concatenate([oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), P0, G0) for b in range(batch)])
+    src = dev(a)
+    shapes = {}
+    for tiles, compact in (("wide", False), ("narrow", False), ("narrow", True), (None, False)):
+        plan = cuda_lib.plan(L, splits=splits, batch=batch, tiles=tiles, compact_tables=compact)
+        shapes[(tiles, compact)] = plan.tile_log2
+        dst = torch.full_like(src, 0x5555555555555555)
+        plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+        assert np.array_equal(host(dst), want), (L, splits, tiles, compact, plan.splits, plan.tile_log2)
+        plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
+        assert np.array_equal(host(dst), a), (L, splits, tiles, compact)
+        plan.close()
+    if splits is not None:  # (the planner's own decomposition differs between small and large plans)
+        small = (m * batch) <= (1 << 20)
+        assert shapes[(None, False)] == (shapes[("narrow", False)] if small else shapes[("wide", False)])
+
+
+def test_tile_shapes_runtime_modulus(cuda_lib, oracle):
+    """narrow tiles of the runtime-modulus (Montgomery) kernels; Goldilocks and Shoup plans keep whole tiles"""
+    import torch
+    for N, g, fixed, has in ((0x3A00000000000001, 3, False, True), (0x0C40000000000001, None, False, True),
+                             (0xFFFFFFFF00000001, 7, False, False), (0x3A00000000000001, 3, True, False)):
+        if g is None:
+            g = dict(OTHER_MODULI)[N]
+        for L in (12, 17, 20):
+            m = 1 << L
+            a = oracle.fill_xorshift(m, SEED + L, N)
+            want = oracle.ntt_forward(a.copy(), N, g)
+            plan = cuda_lib.plan(L, modulus=N, generator=g, fixed_point=fixed)
+            if has and L >= 14:
+                assert max(plan.tile_log2) <= 11, (hex(N), L, plan.tile_log2)
+            if not has:
+                assert plan.tile_log2 == cuda_lib.plan(L, modulus=N, generator=g, fixed_point=fixed, tiles="wide").tile_log2
+            src = dev(a)
+            dst = torch.empty_like(src)
+            plan.forward(dst.data_ptr(), src.data_ptr(), stream())
+            assert np.array_equal(host(dst), want), (hex(N), L)
+            plan.inverse(dst.data_ptr(), dst.data_ptr(), stream())
+            assert np.array_equal(host(dst), a), (hex(N), L)
+            plan.close()
+
+
 @pytest.mark.parametrize("L,batch", [(17, 1), (20, 3), (26, 1)])
 def test_device_calls_capture_into_a_cuda_graph(cuda_lib, oracle, L, batch):
     """The device entry points only enqueue kernels on the caller's stream (no allocation, no synchronisation), so a
