@@ -749,6 +749,12 @@ __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_
   u64 sbase, dbase;
   u32 col0 = 0, row0 = 0;
   tile_origin<Cfg>(prm, tile, sbase, dbase, col0, row0);
+  // Programmatic dependent launch (dispatch.cuh launches every pass with programmatic stream serialisation): the next
+  // kernel in the stream may become resident now, while this grid is still running - it blocks in its own
+  // griddepcontrol.wait below until this grid has completed and its stores are visible.  What a pass of a small plan
+  // saves is the launch latency between two dependent kernels.  Nothing above or below this point and before the wait
+  // touches data another kernel writes (tables and twiddle matrices are read-only once the plan exists).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if constexpr (TWIST == kPostTwist) {
     // consumed by the last stage: start pulling this tile's rows of the matrix (16 N W bytes, contiguous per row)
     // into L2 now
@@ -767,6 +773,7 @@ __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_
         prefetch_l2(q + (((u64)(i / SEG) << prm.twist_full_shift) + (u64)(i % SEG) * 2));
     }
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the kernel before this one has completed
   run_stages<F, Cfg, INVERSE, TWIST>(prm, sm, prm.src + sbase, prm.dst + dbase, col0, row0,
                                      std::make_integer_sequence<int, Cfg::NS>{});
 }
