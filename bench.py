@@ -104,6 +104,29 @@ def archived_traffic(workload, splits, kernel):
 
 # ------------------------------------------------------------------------------------------------
 # clocks: NVML sampled in a thread during the timed region
+def warm_up(torch, step, min_steps, agree_max=None, min_seconds=0.4, max_steps=4000):
+    """At least `min_steps` untimed steps AND about `min_seconds` of GPU work: a GPU that sat idle while the host
+    checked results needs more than three short steps to be back at its clocks (observed on the 2-GPU sharded
+    workload: 3 warm-up steps of 31 ms left the first timed steps 12 % slow).  Every rank runs the same number of steps
+    (the sharded step synchronises the ranks): the count follows from the slowest rank's time for the first
+    `min_steps`, agreed through `agree_max` (an all-reduce MAX)."""
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(min_steps):
+        step(i)
+    torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    if agree_max is not None:
+        elapsed = agree_max(elapsed)
+    extra = 0
+    if elapsed < min_seconds:
+        extra = min(max_steps, int((min_seconds - elapsed) / max(elapsed / min_steps, 1e-6)) + 1)
+    for i in range(extra):
+        step(min_steps + i)
+    torch.cuda.synchronize()
+    return min_steps + extra
+
+
 class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -451,8 +474,12 @@ def bench_sharded(args, lib, torch, dist, rank, world, local_rank, log2_m):
         a2a.forward(mid, src, st)
         a2a.inverse(out, mid, st)
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    def agree_max(v):
+        tv = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return float(tv.item())
+
+    warm_n = warm_up(torch, step, max(args.warmup, 3), agree_max)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -566,7 +593,7 @@ def bench_sharded(args, lib, torch, dist, rank, world, local_rank, log2_m):
             "metric": METRIC, "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(f"dist{log2_m}", world), "log2_m": log2_m, "splits": plan.splits,
+            "config": {"workload": workload_name(f"dist{log2_m}", world), "warmup_steps_run": warm_n, "log2_m": log2_m, "splits": plan.splits,
                        "modulus": "0xfffffc6e80000001", "exchange": a2a.mode,
                        "exchange_fallback_reason": getattr(a2a, "_peer_error", None),
                        "l2": f"per-rank working set {set_bytes * nsets >> 20} MiB, far larger than L2",
@@ -677,8 +704,14 @@ def main():
     assert torch.equal(sets[0][0], sets[0][2]), "inverse(forward(x)) != x"
 
     # ---- timed region --------------------------------------------------------------------------
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    def agree_max(v):
+        if world <= 1:
+            return v
+        tv = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return float(tv.item())
+
+    warm_n = warm_up(torch, step, max(args.warmup, 3), agree_max)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -786,7 +819,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(w, world), "log2_m": log2_m, "batch_per_gpu": batch, "splits": plan.splits,
+            "config": {"workload": workload_name(w, world), "warmup_steps_run": warm_n, "log2_m": log2_m, "batch_per_gpu": batch, "splits": plan.splits,
                        "modulus": "0xfffffc6e80000001",
                        "l2": f"ring of {nsets} buffer sets ({nsets * set_bytes >> 20} MiB) larger than L2, each step touches "
                              "the next set", "parallelism": f"{world}x independent"},
