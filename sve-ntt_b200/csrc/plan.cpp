@@ -110,9 +110,15 @@ struct DeviceGuard {
 // 2^17 28.7 -> 14.4, 2^18 28.9 -> 16.4, 2^19 31.9 -> 21.5, 2^20 33.8 -> 30.8; at 2^21 whole tiles win (56 vs 60 us).
 constexpr int kSmallPlanLog = 20;
 
-int choose_splits(int L, std::vector<int>& out, bool small = false) {
+int choose_splits(int L, std::vector<int>& out, bool small = false, u64 residues = 0) {
   out.clear();
-  if (L <= kMaxRowLog) {
+  if (small && (L == 12 || L == 13) && residues <= (1ull << 17)) {
+    // a few transforms of 2^12 / 2^13: one row pass would be one CTA of a whole tile each (16.4 / 18.5 us); two passes
+    // on narrow tiles spread them over 16 CTAs per pass (7.2 / 8.6 us, still 11.2 us for 16 x 2^13; from 64 x 2^13 on the
+    // single pass wins)
+    out.push_back((L + 1) / 2);
+    out.push_back(L / 2);
+  } else if (L <= kMaxRowLog) {
     out.push_back(L);
   } else if (small && L <= 20) {
     // column pass of at most 2^9 (narrow column tiles stay four columns wide), row pass of at most 2^11
@@ -536,7 +542,7 @@ int xntt_plan_create(xntt_plan** out, const xntt_desc* d) {
     // IterativeNTT / RecursiveNTT static_assert: the product of the radices equals m
     if (sum != d->log2_m) return XNTT_ERR_INVALID;
   } else {
-    const int rc = choose_splits((int)d->log2_m, splits, narrow_tiles);
+    const int rc = choose_splits((int)d->log2_m, splits, narrow_tiles, (u64)(d->batch ? d->batch : 1) << d->log2_m);
     if (rc != XNTT_OK) return rc;
   }
   const u32 shard_count = d->shard_count ? d->shard_count : 1;

@@ -161,6 +161,40 @@ static int emu_launch(const PassParams& prm, unsigned grid) {
     else                                                                  \
       return inverse ? emu_launch<L, false, true>(prm, grid) : emu_launch<L, false, false>(prm, grid);
 
+
+// The pass-kernel instantiations, split over four translation units by logn mod 4: this file is compiled once per
+// part with -DEMU_PART=k (only emu_launch_part<k> is emitted) and once without (everything else).
+int emu_launch_part0(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid);
+int emu_launch_part1(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid);
+int emu_launch_part2(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid);
+int emu_launch_part3(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid);
+
+#ifdef EMU_PART
+#define EMU_PART_NAME2(k) emu_launch_part##k
+#define EMU_PART_NAME(k) EMU_PART_NAME2(k)
+int EMU_PART_NAME(EMU_PART)(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid) {
+  g_map = map;
+  switch (logn) {
+#if EMU_PART == 0
+    EMU_CASE(4) EMU_CASE(8) EMU_CASE(12)
+#elif EMU_PART == 1
+    EMU_CASE(1) EMU_CASE(5) EMU_CASE(9)
+    case 13:
+      if (col) break;
+      return inverse ? emu_launch<13, false, true>(prm, grid) : emu_launch<13, false, false>(prm, grid);
+#elif EMU_PART == 2
+    EMU_CASE(2) EMU_CASE(6) EMU_CASE(10)
+#else
+    EMU_CASE(3) EMU_CASE(7) EMU_CASE(11)
+#endif
+    default:
+      break;
+  }
+  return -1;
+}
+#endif  // EMU_PART
+
+#ifndef EMU_PART
 namespace be {
 
 static std::string g_err = "no error";
@@ -230,17 +264,18 @@ int pointer_is_device(const void*, int* is_device) {
 const char* last_error() { return g_err.c_str(); }
 
 int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid, void*) {
-  g_map = map;
-  switch (logn) {
-    EMU_CASE(1) EMU_CASE(2) EMU_CASE(3) EMU_CASE(4) EMU_CASE(5) EMU_CASE(6) EMU_CASE(7)
-    EMU_CASE(8) EMU_CASE(9) EMU_CASE(10) EMU_CASE(11) EMU_CASE(12)
-    case 13:
-      if (col) break;
-      return inverse ? emu_launch<13, false, true>(prm, grid) : emu_launch<13, false, false>(prm, grid);
-    default:
-      break;
+  // the pass kernels are instantiated in four translation units (compiled in parallel), by logn mod 4
+  int rc = -1;
+  if (logn >= 1 && logn <= 13 && !(col && logn == 13)) {
+    switch (logn & 3) {
+      case 0: rc = emu_launch_part0(logn, col, inverse, map, prm, grid); break;
+      case 1: rc = emu_launch_part1(logn, col, inverse, map, prm, grid); break;
+      case 2: rc = emu_launch_part2(logn, col, inverse, map, prm, grid); break;
+      default: rc = emu_launch_part3(logn, col, inverse, map, prm, grid); break;
+    }
   }
-  g_err = "invalid pass length";
+  if (rc == 0) return 0;
+  g_err = rc < 0 ? "invalid pass length" : "pass kernel not available in this form";
   return 1;
 }
 
@@ -331,4 +366,6 @@ int microbench(int, int, double*, double*) {
 }
 
 }  // namespace be
+#endif  // !EMU_PART
+
 }  // namespace xntt

@@ -33,7 +33,10 @@ def roundtrip(emu, oracle, L, splits=None, batch=1, inverse_factor=None, **kw):
 
 @pytest.mark.parametrize("L", range(1, 14))
 def test_single_pass_sizes(emu, oracle, L):
-    assert roundtrip(emu, oracle, L) == [L]
+    # one row pass; a lone 2^12 / 2^13 transform is cut in two so that narrow tiles spread it over several CTAs
+    assert roundtrip(emu, oracle, L) == ([L] if L < 12 else [(L + 1) // 2, L // 2])
+    assert roundtrip(emu, oracle, L, tiles="wide") == [L]
+    assert roundtrip(emu, oracle, L, splits=[L]) == [L]
 
 
 @pytest.mark.parametrize("L", [14, 15, 16, 17, 18, 20])
@@ -80,9 +83,12 @@ def test_tile_shape_rule_for_large_plans(emu):
     assert batched.tile_log2 == [13]
     small = emu.plan(10, batch=4)
     assert small.tile_log2 == [11]
-    no_variant = emu.plan(12, batch=4)  # a 2^12 row pass has no narrow tile
-    assert no_variant.tile_log2 == [13]
+    no_variant = emu.plan(12, batch=64)  # a 2^12 row pass has no narrow tile; 64 of them are enough CTAs
+    assert no_variant.splits == [12] and no_variant.tile_log2 == [13]
     no_variant.close()
+    few = emu.plan(13, batch=16)
+    assert few.splits == [7, 6] and max(few.tile_log2) <= 11
+    few.close()
     for pl in (big, batched, small):
         pl.close()
 
