@@ -25,10 +25,12 @@ cases = [(13, None, 1, False), (12, None, 2, False), (11, None, 3, False), (10, 
 if len(sys.argv) > 1:
     cases = cases[:int(sys.argv[1])]
 bad = 0
-for L, splits, batch, compact in cases:
+# small plans take narrow tiles by default: every case runs on both tile shapes
+cases = [c + (t,) for c in cases for t in ((None, "wide") if c[0] <= 20 else (None,))]
+for L, splits, batch, compact, tiles in cases:
     m = 1 << L
     a = orc.fill_xorshift(m * batch, 99 + L, P0)
-    plan = lib.plan(L, splits=splits, batch=batch, compact_tables=compact)
+    plan = lib.plan(L, splits=splits, batch=batch, compact_tables=compact, tiles=tiles)
     d = torch.from_numpy(a.view(np.int64)).cuda()
     o = torch.empty_like(d)
     plan.forward(o.data_ptr(), d.data_ptr(), st)
@@ -41,7 +43,7 @@ for L, splits, batch, compact in cases:
     # fused point-wise product path
     plan.forward_multiply(o.data_ptr(), d.data_ptr(), d.data_ptr(), st)
     torch.cuda.synchronize()
-    print(L, plan.splits, batch, "compact" if compact else "matrix", "ok" if ok else "MISMATCH", flush=True)
+    print(L, plan.splits, plan.tile_log2, batch, "compact" if compact else "matrix", "ok" if ok else "MISMATCH", flush=True)
     bad += 0 if ok else 1
     plan.close()
 # runtime-modulus kernels (Montgomery and Shoup) and the multi-GPU plan with every rank on this device (peer stores,
