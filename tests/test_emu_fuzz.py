@@ -1,6 +1,6 @@
 # SPDX-License-Identifier: Apache-2.0
 """Random plan shapes on the host emulator against the oracle: length, explicit splits, batch, modulus, twiddle-table
-form and inverse_factor drawn from a fixed seed (a few hundred plans; `python tests/test_emu_fuzz.py SEED SECONDS`
+form, tile shape and inverse_factor drawn from a fixed seed (a few hundred plans; `python tests/test_emu_fuzz.py SEED SECONDS`
 keeps drawing).  Forward, scaled inverse and the fused point-wise product are compared word for word."""
 import random
 import sys
@@ -12,8 +12,8 @@ import pytest
 MODS = [(0xFFFFFC6E80000001, 3), (0xFFFFFFFF00000001, 7), (0x3A00000000000001, 3), (0xA3B25F400C7A8001, 5)]
 
 
-def draw(rng):
-    L = rng.randint(2, 16)
+def draw(rng, max_l=16):
+    L = rng.randint(2, max_l)
     parts = rng.choice([1, 2, 2, 3])
     splits = None
     if parts > 1:
@@ -25,7 +25,7 @@ def draw(rng):
     if (N - 1) % (1 << L):
         return None
     return dict(L=L, splits=splits, batch=rng.choice([1, 1, 2, 3, 5]), N=N, g=g, compact=rng.random() < 0.4,
-                invf=rng.choice([None, 1, 12345]), seed=rng.getrandbits(60))
+                invf=rng.choice([None, 1, 12345]), seed=rng.getrandbits(60), tiles=rng.choice([None, None, "wide", "narrow"]))
 
 
 def check(emu, pkg, orc, c):
@@ -33,7 +33,7 @@ def check(emu, pkg, orc, c):
     m = 1 << L
     try:
         plan = emu.plan(L, modulus=N, generator=g, splits=c["splits"], batch=batch, compact_tables=c["compact"],
-                        inverse_factor=c["invf"])
+                        inverse_factor=c["invf"], tiles=c["tiles"])
     except pkg.XnttError as e:
         assert e.status in (pkg.ERR_INVALID, pkg.ERR_UNSUPPORTED), c  # shapes without a tile layout are refused
         return False

@@ -638,6 +638,48 @@ def test_tile_shapes_runtime_modulus(cuda_lib, oracle):
             plan.close()
 
 
+@pytest.mark.parametrize("seed", [21, 22])
+def test_random_plans_on_gpu(cuda_lib, pkg, oracle, seed):
+    """The emulator's fuzz (tests/test_emu_fuzz.py: random length up to 2^19, explicit splits, batch, modulus, twiddle form,
+    tile shape, inverse_factor from a fixed seed) on the GPU: forward, scaled inverse and the fused point-wise product,
+    word for word against the oracle."""
+    import random
+    import torch
+    from test_emu_fuzz import draw
+    rng = random.Random(seed)
+    done = 0
+    while done < 100:
+        c = draw(rng, max_l=19)
+        if c is None:
+            continue
+        L, N, g, batch = c["L"], c["N"], c["g"], c["batch"]
+        m = 1 << L
+        try:
+            plan = cuda_lib.plan(L, modulus=N, generator=g, splits=c["splits"], batch=batch, compact_tables=c["compact"],
+                                 inverse_factor=c["invf"], tiles=c["tiles"])
+        except pkg.XnttError as e:
+            assert e.status in (pkg.ERR_INVALID, pkg.ERR_UNSUPPORTED), c
+            continue
+        a = oracle.fill_xorshift(m * batch, c["seed"], N)
+        src = dev(a)
+        out = torch.full_like(src, 0x5555555555555555)
+        plan.forward(out.data_ptr(), src.data_ptr(), stream())
+        got = host(out)
+        for b in range(batch):
+            assert np.array_equal(got[b * m:(b + 1) * m], oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), N, g)), (c, plan.splits, plan.tile_log2)
+        back = torch.empty_like(src)
+        plan.inverse(back.data_ptr(), out.data_ptr(), stream())
+        f = m if c["invf"] is None else c["invf"]
+        assert np.array_equal(host(back), oracle.pointwise_mul(a, np.full_like(a, (m * pow(f, -1, N)) % N), N)), c
+        bm = oracle.fill_xorshift(m * batch, 7, N)
+        fm = torch.empty_like(src)
+        plan.forward_multiply(fm.data_ptr(), src.data_ptr(), dev(bm).data_ptr(), stream())
+        want = oracle.pointwise_mul(oracle.pointwise_mul(got, bm, N), np.full_like(a, pow(1 << 64, -1, N)), N)
+        assert np.array_equal(host(fm), want), c
+        plan.close()
+        done += 1
+
+
 @pytest.mark.parametrize("L,batch", [(17, 1), (20, 3), (26, 1)])
 def test_device_calls_capture_into_a_cuda_graph(cuda_lib, oracle, L, batch):
     """The device entry points only enqueue kernels on the caller's stream (no allocation, no synchronisation), so a
