@@ -638,6 +638,37 @@ def test_tile_shapes_runtime_modulus(cuda_lib, oracle):
             plan.close()
 
 
+@pytest.mark.parametrize("L,batch,tiles", [(10, 1, None), (13, 1, None), (17, 1, None), (19, 1, "wide"), (20, 1, None), (21, 1, None),
+                                           (24, 1, None)])
+def test_dependent_launch_chains(cuda_lib, L, batch, tiles):
+    """Every pass is launched as a programmatic dependent of the kernel before it: a chain of in-place transforms enqueued
+    back to back must equal the same chain with a synchronisation after every call, and forward / inverse ping-pongs (in
+    place and between two buffers) must return their input (tools/stress_chain.py is the long version)."""
+    import torch
+    m = 1 << L
+    reps = 60 if L <= 21 else 10
+    plan = cuda_lib.plan(L, batch=batch, tiles=tiles)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(L)
+    x0 = torch.randint(0, 2**62, (m * batch,), dtype=torch.int64, device="cuda", generator=gen)
+    x, y = x0.clone(), x0.clone()
+    for _ in range(reps):
+        plan.forward(x.data_ptr(), x.data_ptr(), stream())
+    for _ in range(reps):
+        plan.forward(y.data_ptr(), y.data_ptr(), stream())
+        torch.cuda.synchronize()
+    assert torch.equal(x, y)
+    p, q = x0.clone(), torch.empty_like(x0)
+    for _ in range(reps):
+        plan.forward(q.data_ptr(), p.data_ptr(), stream())
+        plan.inverse(p.data_ptr(), q.data_ptr(), stream())
+        plan.forward(p.data_ptr(), p.data_ptr(), stream())
+        plan.inverse(p.data_ptr(), p.data_ptr(), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(p, x0)
+    plan.close()
+
+
 @pytest.mark.parametrize("seed", [21, 22])
 def test_random_plans_on_gpu(cuda_lib, pkg, oracle, seed):
     """The emulator's fuzz (tests/test_emu_fuzz.py: random length up to 2^19, explicit splits, batch, modulus, twiddle form,
