@@ -233,6 +233,11 @@ __device__ __forceinline__ ulonglong2 ld_stream2(const u64* p) {
 #ifndef XNTT_TMA_ROWS
 #define XNTT_TMA_ROWS 0
 #endif
+// XNTT_PREFETCH_TABLE: prefetch the pass's twiddle table into L1 ahead of griddepcontrol.wait.  Measured on B200: no gain
+// (one 2^10 .. 2^19 transform within 0.1 us either way, 2^20 27.8 -> 28.5 us, 2^24 inverse 382.5 -> 387.7 us), so it stays off.
+#ifndef XNTT_PREFETCH_TABLE
+#define XNTT_PREFETCH_TABLE 0
+#endif
 
 #if XNTT_TMA_ROWS && !defined(XNTT_HOST_EMU)
 // The tile (2^13 contiguous residues = 64 KiB) is described to the TMA unit as 512 rows of 16 residues (128 bytes) with
@@ -773,6 +778,11 @@ __global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_
         prefetch_l2(q + (((u64)(i / SEG) << prm.twist_full_shift) + (u64)(i % SEG) * 2));
     }
   }
+#if XNTT_PREFETCH_TABLE
+  // the pass's own twiddle table (read-only) into L1 while waiting for the kernel before: one 128-byte line per thread step
+  for (int e = threadIdx.x * 8; e < (INVERSE ? Cfg::N : Cfg::N / 2); e += kThreads * 8)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(prm.tw + e));
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the kernel before this one has completed
   run_stages<F, Cfg, INVERSE, TWIST>(prm, sm, prm.src + sbase, prm.dst + dbase, col0, row0,
                                      std::make_integer_sequence<int, Cfg::NS>{});
