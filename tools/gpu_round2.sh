@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.draw --format=csv > gp
 nproc > gpurun_out/nproc.txt; lscpu | head -20 >> gpurun_out/nproc.txt
 timeout 1700 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -5 gpurun_out/pytest_gpu.log
-timeout 120 tools/lab/bfly_lab 500 > gpurun_out/bfly_lab.jsonl 2>&1; echo "lab rc=$?"; cat gpurun_out/bfly_lab.jsonl
+timeout 120 tools/lab/_build/bfly_lab 500 > gpurun_out/bfly_lab.jsonl 2>&1; echo "lab rc=$?"; cat gpurun_out/bfly_lab.jsonl
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/bench.err
 python - <<'PY'
