@@ -34,6 +34,9 @@ int event_destroy(void* event);
 int event_record(void* event, void* stream);
 int stream_wait_event(void* stream, void* event);
 int pointer_is_device(const void* p, int* is_device);
+// *dev = the address kernels can use for page-locked, mapped host memory at p (with unified addressing: p itself),
+// nullptr for pageable host memory (or anything else a kernel must not touch)
+int host_device_pointer(const void* p, void** dev);
 const char* last_error();
 
 // map = true: use prm.smap / prm.dmap (generalised addressing; built for kP0 only)

@@ -264,6 +264,16 @@ int pointer_is_device(const void* p, int* is_device) {
   *is_device = (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
   return 0;
 }
+int host_device_pointer(const void* p, void** dev) {
+  *dev = nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (a.type == cudaMemoryTypeHost && a.devicePointer != nullptr) *dev = a.devicePointer;
+  return 0;
+}
 const char* last_error() { return g_err.c_str(); }
 
 int launch_pass(int logn, bool col, bool inverse, bool map, const PassParams& prm, unsigned grid, void* stream) {

@@ -430,6 +430,28 @@ def test_transpose_contract(emu):
         assert np.array_equal(b[:, :dim], a[:, :dim].T)
 
 
+@pytest.mark.parametrize("L,batch,splits", [(10, 1, None), (13, 1, None), (13, 1, [13]), (11, 4, None), (5, 7, None), (12, 2, [5, 7]),
+                                            (14, 1, None)])
+def test_host_entry_points_small(emu, oracle, L, batch, splits):
+    """Single-pass plans of up to 64 KiB run straight on the caller's mapped host buffers (the emulator counts every host
+    buffer as mapped); everything else is staged.  Out of place and in place."""
+    m = 1 << L
+    a = oracle.fill_xorshift(m * batch, SEED + L, P0)
+    want = np.concatenate([oracle.ntt_forward(a[b * m:(b + 1) * m].copy(), P0, G0) for b in range(batch)])
+    plan = emu.plan(L, batch=batch, splits=splits)
+    out, back = np.empty_like(a), np.empty_like(a)
+    plan.forward_host(out.ctypes.data, a.ctypes.data)
+    assert np.array_equal(out, want)
+    plan.inverse_host(back.ctypes.data, out.ctypes.data)
+    assert np.array_equal(back, a)
+    buf = a.copy()
+    plan.forward_host(buf.ctypes.data, buf.ctypes.data)
+    assert np.array_equal(buf, want)
+    plan.inverse_host(buf.ctypes.data, buf.ctypes.data)
+    assert np.array_equal(buf, a)
+    plan.close()
+
+
 @pytest.mark.parametrize("L,batch,splits", [(20, 5, None), (16, 200, None), (22, 1, None), (22, 1, [7, 7, 8])])
 def test_host_entry_point_pipelines(emu, oracle, L, batch, splits):
     """xntt_forward_host / xntt_inverse_host on buffers large enough for the chunk pipelines: a batch cut into

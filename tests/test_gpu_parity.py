@@ -204,12 +204,13 @@ def test_host_entry_points(cuda_lib, oracle):
     plan.close()
 
 
-@pytest.mark.parametrize("L,batch", [(16, 1), (12, 5), (20, 2), (9, 3), (18, 37), (22, 1)])
+@pytest.mark.parametrize("L,batch", [(16, 1), (12, 5), (20, 2), (9, 3), (18, 37), (22, 1), (10, 1), (13, 1), (11, 4), (5, 7)])
 def test_host_entry_points_page_locked(cuda_lib, oracle, L, batch):
     """Page-locked host buffers (what bench.py's e2e leg and sventt::PageMemory hand in): same words as the
     pageable route, also in place, batched (large batches flow through the copy / transform / copy chunk pipeline,
     here 37 x 2^18 = 8 ragged chunks; one 2^22 transform has its row pass cut into chunks that overlap the copies) and
-    for single-pass plans."""
+    for single-pass plans.  Single-pass plans of up to 64 KiB work on the page-locked buffers themselves (2^10, 4 x 2^11,
+    7 x 2^5: straight from host to host, no staging)."""
     import torch
     m = 1 << L
     a = oracle.fill_xorshift(m * batch, SEED + L, P0)
