@@ -473,6 +473,46 @@ __device__ __forceinline__ void apply_pre_twist(const F& f, const PassParams& pr
   }
 }
 
+// XNTT_SHFL_FUSE (measured variant, off in the product build): the innermost exchange of a row pass with one residue per
+// slot - the 8 x 8 transposition between the stride-8 and the stride-1 radix-8 stage, which connects 8 consecutive lanes
+// - goes through warp shuffles instead of shared memory, and the two stages run back to back on the same registers
+// (a radix-64 step: one shared-memory round trip and one __syncwarp less, 24 SHFL + their selects more).  Measured on
+// B200 (tools/gpu_variants.py, profiles/r4_variants_shfl.log).
+#ifndef XNTT_SHFL_FUSE
+#define XNTT_SHFL_FUSE 0
+#endif
+template <class Cfg>
+__host__ __device__ constexpr bool shfl_fused() {
+#if XNTT_SHFL_FUSE && !defined(XNTT_HOST_EMU)
+  return !Cfg::COL && Cfg::C == 1 && Cfg::LOGRN == 3 && Cfg::NS >= 3 && !Cfg::TMA;
+#else
+  return false;
+#endif
+}
+#if XNTT_SHFL_FUSE && !defined(XNTT_HOST_EMU)
+// new x[r] of lane j = old x[j] of lane r, over every aligned group of 8 lanes: three rounds, each swapping one bit of
+// the register index with one bit of the lane index
+__device__ __forceinline__ void shfl_transpose8(u64 (&x)[8][1]) {
+  const unsigned lane = threadIdx.x;
+#pragma unroll
+  for (int s = 1; s < 8; s <<= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r & s) continue;
+      const u64 send = up ? x[r][0] : x[r | s][0];
+      const u64 recv = __shfl_xor_sync(0xffffffffu, send, s);
+      if (up)
+        x[r][0] = recv;
+      else
+        x[r | s][0] = recv;
+    }
+  }
+}
+#else
+__device__ __forceinline__ void shfl_transpose8(u64 (&)[8][1]) {}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Forward radix-R register network (Cooley-Tukey, block-indexed twiddles).
 template <class F, int LOGR, int C, bool FIRST>
@@ -569,11 +609,44 @@ __device__ __forceinline__ void stage_barrier() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// what the last forward stage does with its R results (stride 2^logs) before they leave the tile
+template <class F, class Cfg, int TWIST, int R>
+__device__ __forceinline__ void fwd_finish(const F& f, const PassParams& prm, u64 (&x)[R][Cfg::C], u64* gdst, u32 col0,
+                                           u32 row0, int k0, int logs, int p) {
+  if constexpr (TWIST == kCompactTwist || TWIST == kFullTwist) {
+    apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, logs, col0 + p * Cfg::C);
+  } else if constexpr (TWIST == kPointwise || TWIST == kPrePointwise) {
+    // fused point-wise product of a polynomial multiply
+    // (examples/magic-series/gaussian-polynomial.hpp:201-212); the Montgomery product is canonical
+    u64 b[R][Cfg::C];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < Cfg::C; ++c) {
+        // rows past the end of a ragged last tile hold nothing to multiply with
+        const bool ok = Cfg::COL || row0 + (u32)(p * Cfg::C + c) < prm.rows;
+        b[r][c] = ok ? (prm.pointwise + (gdst - prm.dst))[gofs<Cfg>(prm, prm.dmap, k0 + (r << logs), p, c)] : 0ull;
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], b[r][c], f.companion(b[r][c]));
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.canon(x[r][c]);
+  }
+  gmem_store<Cfg, R>(prm, gdst, row0, k0, logs, p, x);
+}
+
 template <class F, class Cfg, int TWIST, int J>
 __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<Cfg::C>::type* sm,
                                           const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
   const F f = make_field<F>(prm.field);
   constexpr int NS = Cfg::NS;
+  constexpr bool FUSE = shfl_fused<Cfg>();       // stages NS-2 and NS-1 back to back, exchange by warp shuffles
+  if constexpr (FUSE && J == NS - 1) return;     // ran inside stage NS-2
   constexpr int LOGR = (J == 0) ? Cfg::LOGR1 : Cfg::LOGRN;
   constexpr int R = 1 << LOGR;
   constexpr int LOGS = Cfg::LOGRN * (NS - 1 - J);
@@ -608,37 +681,21 @@ __device__ __forceinline__ void fwd_stage(const PassParams& prm, typename Slot<C
       smem_load<Cfg, LOGS, R>(sm, k0, p, x);
     }
     fwd_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, B);
-    if constexpr (J == NS - 1) {
-      if constexpr (TWIST == kCompactTwist || TWIST == kFullTwist) {
-        apply_twist<F, Cfg, R, TWIST>(f, prm, x, k0, LOGS, col0 + p * Cfg::C);
-      } else if constexpr (TWIST == kPointwise || TWIST == kPrePointwise) {
-        // fused point-wise product of a polynomial multiply
-        // (examples/magic-series/gaussian-polynomial.hpp:201-212); the Montgomery product is canonical
-        u64 b[R][Cfg::C];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int c = 0; c < Cfg::C; ++c) {
-            // rows past the end of a ragged last tile hold nothing to multiply with
-            const bool ok = Cfg::COL || row0 + (u32)(p * Cfg::C + c) < prm.rows;
-            b[r][c] = ok ? (prm.pointwise + (gdst - prm.dst))[gofs<Cfg>(prm, prm.dmap, k0 + (r << LOGS), p, c)] : 0ull;
-          }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], b[r][c], f.companion(b[r][c]));
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.canon(x[r][c]);
+    if constexpr (FUSE && J == NS - 2) {
+      // task t of the last stage owns the 8 consecutive residues 8 t .. 8 t + 7: exactly what the 8 lanes of this
+      // task's group hold between them
+      if constexpr (R == 8 && Cfg::C == 1) {
+        shfl_transpose8(x);
+        fwd_network<F, 3, Cfg::C, false>(f, x, prm.tw, t);
+        fwd_finish<F, Cfg, TWIST, R>(f, prm, x, gdst, col0, row0, t << 3, 0, p);
       }
-      gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
+    } else if constexpr (J == NS - 1) {
+      fwd_finish<F, Cfg, TWIST, R>(f, prm, x, gdst, col0, row0, k0, LOGS, p);
     } else {
       smem_store<Cfg, LOGS, R>(sm, k0, p, x);
     }
   }
-  if constexpr (J != NS - 1) stage_barrier<barrier_group<Cfg, false, J>()>();
+  if constexpr (J != NS - 1 && !(FUSE && J == NS - 2)) stage_barrier<barrier_group<Cfg, false, J>()>();
 }
 
 template <class F, class Cfg, int TWIST, int J>
@@ -646,6 +703,11 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
                                           const u64* gsrc, u64* gdst, u32 col0, u32 row0) {
   const F f = make_field<F>(prm.field);
   constexpr int NS = Cfg::NS;
+  constexpr bool FUSE = shfl_fused<Cfg>();  // stages 0 and 1 back to back, exchange by warp shuffles
+  if constexpr (FUSE && J == 1) {
+    stage_barrier<barrier_group<Cfg, true, 1>()>();  // ran inside stage 0; its results are in shared memory
+    return;
+  }
   // inverse stage J mirrors forward stage NS-1-J
   constexpr int LOGR = (J == NS - 1) ? Cfg::LOGR1 : Cfg::LOGRN;
   constexpr int R = 1 << LOGR;
@@ -685,7 +747,14 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
       smem_load<Cfg, LOGS, R>(sm, k0, p, x);
     }
     inv_network<F, LOGR, Cfg::C, J == 0>(f, x, prm.tw, LOGS, i);
-    if constexpr (J == NS - 1 && TWIST == kPostTwist) {
+    if constexpr (FUSE && J == 0) {
+      // stage 1 (stride 8): task t owns residues 64 (t >> 3) + (t & 7) + 8 r - one from each lane of its group of 8
+      if constexpr (R == 8 && Cfg::C == 1) {
+        shfl_transpose8(x);
+        inv_network<F, 3, Cfg::C, false>(f, x, prm.tw, 3, t & 7);
+        smem_store<Cfg, 3, R>(sm, ((t >> 3) << 6) + (t & 7), p, x);
+      }
+    } else if constexpr (J == NS - 1 && TWIST == kPostTwist) {
       // the twiddle matrix of the column pass behind this row pass (and 1/inverse_factor with it); canonical result
       apply_pre_twist<F, Cfg, R>(f, prm, x, k0, LOGS, row0 + (u32)(p * Cfg::C));
       gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
@@ -706,7 +775,7 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
       smem_store<Cfg, LOGS, R>(sm, k0, p, x);
     }
   }
-  if constexpr (J != NS - 1) stage_barrier<barrier_group<Cfg, true, J>()>();
+  if constexpr (J != NS - 1 && !(FUSE && J == 0)) stage_barrier<barrier_group<Cfg, true, J>()>();
 }
 
 template <class F, class Cfg, bool INVERSE, int TWIST, int... Js>

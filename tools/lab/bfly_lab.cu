@@ -9,6 +9,7 @@
 #include "field.cuh"
 #include "field2.cuh"
 #include "field3.cuh"
+#include "field4.cuh"
 
 using namespace xntt;
 
@@ -59,6 +60,10 @@ __device__ __forceinline__ void bfly(u64& x0, u64& x1, u64 w, u64 wp) {
     lab::bf_fp64<0, 1, true>(x0, x1, w, wp);
   } else if constexpr (V == 22) {
     lab::bf_fp64<1, 1, false>(x0, x1, w, wp);
+  } else if constexpr (V == 23) {
+    lab::bf_v23(x0, x1, w, wp);
+  } else if constexpr (V == 24) {
+    lab::bf_v24(x0, x1, w, wp);
   }
 }
 
@@ -268,6 +273,8 @@ int main(int argc, char** argv) {
   if (only < 0 || only == 19) rc |= run<19, 2>("v19_h2_fp64_magic", iters);
   if (only < 0 || only == 22) rc |= run<22, 2>("v22_h2_fp64_magic_fix_alu_sum", iters);
   if (only < 0 || only == 20) rc |= run<20, 2>("v20_h2_int_2wide", iters);
+  if (only < 0 || only == 23) rc |= run<23, 2>("v23_three_operand_int128", iters);
+  if (only < 0 || only == 24) rc |= run<24, 2>("v24_three_operand_chains", iters);
   if (only < 0 || only == 6) rc |= run<6, 2>("v6_probe_nofix", iters, false);
   if (only < 0 || only == 7) rc |= run<7, 2>("v7_probe_mont_only", iters, false);
   return rc;
