@@ -64,6 +64,16 @@ __device__ __forceinline__ void bfly(u64& x0, u64& x1, u64 w, u64 wp) {
     lab::bf_v23(x0, x1, w, wp);
   } else if constexpr (V == 24) {
     lab::bf_v24(x0, x1, w, wp);
+  } else if constexpr (V == 25) {
+    lab::bf_v25<0>(x0, x1, w, wp);
+  } else if constexpr (V == 26) {
+    lab::bf_v25<1>(x0, x1, w, wp);
+  } else if constexpr (V == 27) {
+    lab::bf_v27(x0, x1, w, wp);
+  } else if constexpr (V == 28) {
+    lab::bf_v28(x0, x1, w, wp);
+  } else if constexpr (V == 29) {
+    lab::bf_v29(x0, x1, w, wp);
   }
 }
 
@@ -259,7 +269,8 @@ int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 500;
   int rc = 0;
   const int only = argc > 2 ? atoi(argv[2]) : -1;
-  if (only < 0 || only == 9) rc |= run<9, 2>("v9_field_cuh_now", iters);
+  if (only < 0 || only == 0) rc |= run<0, 2>("v0_field_cuh_product", iters);  // FieldOps::ct_butterfly as shipped
+  if (only < 0 || only == 9) rc |= run<9, 2>("v9_field_cuh_two_sided", iters);  // mont_parts + sub_borrow_mask (until r3)
   if (only < 0 || only == 14) rc |= run<14, 2>("v14_deferred_repairs", iters);
   if (only < 0 || only == 12) rc |= run<12, 2>("v12_lhi_from_qP", iters);
   if (only < 0 || only == 13) rc |= run<13, 2>("v13_lhi_from_qP_q1P0_shifts", iters);
@@ -275,6 +286,11 @@ int main(int argc, char** argv) {
   if (only < 0 || only == 20) rc |= run<20, 2>("v20_h2_int_2wide", iters);
   if (only < 0 || only == 23) rc |= run<23, 2>("v23_three_operand_int128", iters);
   if (only < 0 || only == 24) rc |= run<24, 2>("v24_three_operand_chains", iters);
+  if (only < 0 || only == 25) rc |= run<25, 2>("v25_q1_chained", iters);
+  if (only < 0 || only == 26) rc |= run<26, 2>("v26_q1_chained_prmt_pairs", iters);
+  if (only < 0 || only == 27) rc |= run<27, 2>("v27_glue_pinned_to_alu", iters);
+  if (only < 0 || only == 28) rc |= run<28, 2>("v28_q1_chained_carry2_as_borrow", iters);
+  if (only < 0 || only == 29) rc |= run<29, 2>("v29_v28_carry_words_without_not", iters);
   if (only < 0 || only == 6) rc |= run<6, 2>("v6_probe_nofix", iters, false);
   if (only < 0 || only == 7) rc |= run<7, 2>("v7_probe_mont_only", iters, false);
   return rc;
