@@ -307,6 +307,18 @@ struct FieldOps : K {
     return mont(v, o, companion(o));
   }
 
+  // canon(v) when `on`, v itself otherwise - branch-free for the 64-bit moduli (one more predicate input of the select)
+  __device__ __forceinline__ u64 canon_if(u64 v, bool on) const {
+    const u64 P = this->p();
+    if ((P >> 63) != 0) {
+      u64 t;
+      u32 c;
+      add_carry_plus(v, this->c(), 0u, t, c);
+      return (c != 0 && on) ? t : v;
+    }
+    return on ? canon(v) : v;
+  }
+
   // Cooley-Tukey butterfly on lazy values: (x0, x1) <- (x0 + x1*omega, x0 - x1*omega).
   // x0, x1 lazy in, lazy out.  The Montgomery correction is folded into the add/sub repair:
   // with u = (h1 - h2) mod 2^64 and br its borrow, x1*omega = u - br*2^64, hence
@@ -378,6 +390,7 @@ struct FieldShoup : FieldOps<RuntimeModulus> {
     const u64 P = this->p();
     return csub(csub(v, 2 * P), P);
   }
+  __device__ __forceinline__ u64 canon_if(u64 v, bool on) const { return on ? canon(v) : v; }
   // (x0, x1) <- (x0 + x1 * omega, x0 - x1 * omega), all values in [0, 4N)
   __device__ __forceinline__ void ct_butterfly(u64& x0, u64& x1, u64 w, u64 wp) const {
     const u64 P2 = 2 * this->p();

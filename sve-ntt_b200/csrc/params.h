@@ -106,6 +106,9 @@ struct PassParams {
   const u64* pointwise;  // forward row pass: multiply output word i by pointwise[i] * 2^-64 (fused
                          // PAdic64::multiply_normalize against a to_montgomery'd spectrum), or null
   u32 narrow;            // run the narrow-tile kernel of this pass length (pass_logw(logn, true); plain addressing only)
+  u32 lazy_out;          // inverse column pass: store lazy residues (any u64 standing for v mod P) - set by the planner
+                         // when the pass that consumes them begins with the Montgomery product by its own twiddle
+                         // (the outer column pass of a three-pass plan), which takes any 64-bit value
 };
 // fields whose kernels exist in the narrow-tile form: the production prime and runtime Montgomery
 inline bool field_has_narrow(const FieldConsts& fc) {

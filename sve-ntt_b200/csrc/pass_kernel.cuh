@@ -631,6 +631,12 @@ __device__ __forceinline__ void fwd_finish(const F& f, const PassParams& prm, u6
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], b[r][c], f.companion(b[r][c]));
+  } else if constexpr (Cfg::COL && (TWIST == kNoTwist || TWIST == kColPre)) {
+    // A forward column pass that leaves its six-step twiddle to the pass behind it stores LAZY residues: that pass
+    // (row pass with kPreTwist / kPrePointwise, column pass with kColPre) begins with the Montgomery product by the
+    // matrix entry, which takes any 64-bit value and returns a canonical one - canonicalising here would be six
+    // instructions per residue for nothing (2^11 columns of a 2^24 plan: 3.6 % of the pass).  Forward column passes
+    // never produce a plan's final output (the last pass is a row pass).
   } else {
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -765,10 +771,12 @@ __device__ __forceinline__ void inv_stage(const PassParams& prm, typename Slot<C
 #pragma unroll
           for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.mont(x[r][c], prm.scale);
       } else {
+        // an inner column pass of a three-pass plan may store lazy residues (PassParams::lazy_out)
+        const bool on = !(Cfg::COL && prm.lazy_out != 0);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int c = 0; c < Cfg::C; ++c) x[r][c] = f.canon(x[r][c]);
+          for (int c = 0; c < Cfg::C; ++c) x[r][c] = Cfg::COL ? f.canon_if(x[r][c], on) : f.canon(x[r][c]);
       }
       gmem_store<Cfg, R>(prm, gdst, row0, k0, LOGS, p, x);
     } else {

@@ -196,6 +196,16 @@ void set_forward_handover(const xntt_plan* pl, size_t i, PassParams& prm) {
   }
 }
 
+// Inverse column pass i > 0: the pass that consumes its output (column pass i - 1, executed next) applies its own
+// six-step twiddle while loading, i.e. begins with a Montgomery product - which takes any 64-bit value - so pass i may
+// skip canonicalising what it stores (PassParams::lazy_out).
+bool inverse_output_may_stay_lazy(const xntt_plan* pl, size_t i) {
+  if (i == 0 || !pl->passes[i].col) return false;
+  const PassDesc& c = pl->passes[i - 1];
+  if (!c.col || row_applies_twist(pl, i - 1, true)) return false;
+  return c.inv_full != nullptr || (c.inv_lo != nullptr && c.inv_hi != nullptr);
+}
+
 // One pass.  `count_override` (when non-zero) replaces the number of outer blocks / rows: the row
 // half of a sharded plan only holds 1/shard_count of them.
 int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* src, void* st,
@@ -225,6 +235,7 @@ int run_pass(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const u64* s
     prm.twist_full_shift = (u32)log2u(inner);  // columns per row of the stored matrix (a rank's block if sharded)
     if (row_applies_twist(pl, i, inverse)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
     if (!inverse) set_forward_handover(pl, i, prm);
+    prm.lazy_out = (inverse && inverse_output_may_stay_lazy(pl, i)) ? 1u : 0u;
     prm.twist_col0 = sharded_first ? (u32)(inner * pl->shard_rank) : 0u;
     const u64 tiles = outer * prm.tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
@@ -488,6 +499,7 @@ int run_pass_mapped(const xntt_plan* pl, size_t i, bool inverse, u64* dst, const
     prm.twist_full_shift = (u32)ps.log_inner - ((i == 0 && pl->shard_count > 1) ? (u32)log2u(pl->shard_count) : 0u);
     if (row_applies_twist(pl, i, inverse)) prm.twist_lo = prm.twist_hi = prm.twist_full = nullptr;
     if (!inverse) set_forward_handover(pl, i, prm);
+    prm.lazy_out = (inverse && inverse_output_may_stay_lazy(pl, i)) ? 1u : 0u;
     prm.twist_col0 = twist_col0;
     const u64 tiles = units * tiles_per_outer;
     if (tiles == 0 || tiles > 0x7fffffffull) return XNTT_ERR_INVALID;
