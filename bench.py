@@ -43,7 +43,7 @@ SEED = 0x9E3779B97F4A7C15
 METRIC = "64-bit NTT throughput (forward+inverse round trip)"
 NVLINK_PEAK_GBS, NVLINK_NOMINAL_GBS = 770.0, 900.0  # B200_PROFILING.md: measured peer copy / nominal, per direction
 # ncu --set full capture of the default command, per launch (profiles/, archival: not measured in this run)
-TRAFFIC_PROFILE = "profiles/r3_ncu_pass_kernels.json"
+TRAFFIC_PROFILE = "profiles/r4_ncu_pass_kernels.json"
 
 
 def parse_args():
