@@ -126,7 +126,9 @@ int xntt_forward_multiply(const xntt_plan* plan, uint64_t* dst, const uint64_t* 
                           void* stream);
 
 /* One pass of a plan on its own (profiling / per-kernel timing): pass index in forward order,
- * inverse != 0 runs the inverse kernel of that pass.  In place or src -> dst like the full calls. */
+ * inverse != 0 runs the inverse kernel of that pass.  In place or src -> dst like the full calls.
+ * What a pass leaves between two passes is an internal format: a column pass whose successor begins with a modular
+ * product stores residues as any 64-bit value congruent to them ("lazy"); only complete transforms promise [0, p). */
 int xntt_run_pass(const xntt_plan* plan, uint32_t pass, int inverse, uint64_t* dst, const uint64_t* src,
                   void* stream);
 
