@@ -139,15 +139,15 @@ cudaError_t launch_kernel(const PassParams& prm, unsigned grid, cudaStream_t st)
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
 #ifndef XNTT_CARVE_TILES
-#define XNTT_CARVE_TILES XNTT_MINB
+#define XNTT_CARVE_TILES pass_minb(COL, C, TWIST == kNoTwist)
 #endif
-#if XNTT_CARVE_TILES > 2
-    // room for XNTT_MINB resident tiles and not more: what is left of the 228 KiB stays L1, which the twiddle
-    // tables live in (measured: 2^24 forward 433 us with the default split, 506 us with L1 squeezed to 32 KiB)
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             (int)((XNTT_CARVE_TILES * (Cfg::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
-    if (e != cudaSuccess) return e;
-#endif
+    if constexpr (XNTT_CARVE_TILES > 2) {
+      // room for that many resident tiles and not more: what is left of the 228 KiB stays L1, which the twiddle
+      // tables live in (measured: 2^24 forward 433 us with the default split, 506 us with L1 squeezed to 32 KiB)
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               (int)((XNTT_CARVE_TILES * (Cfg::kSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+      if (e != cudaSuccess) return e;
+    }
     attr_done.store(true, std::memory_order_release);
   }
   // programmatic stream serialisation: this grid may become resident while the kernel before it in the stream is

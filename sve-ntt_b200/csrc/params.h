@@ -31,6 +31,14 @@ constexpr int tile_logw(int logn) {
 #ifndef XNTT_MINB
 #define XNTT_MINB 2
 #endif
+// ... except plain row passes with one residue per slot (2^13 rows, narrow 2^11 rows; no twiddle matrix, no point-wise
+// product): three resident CTAs at 80 registers.  Measured on B200 (profiles/r4_variants_row3.log): 2048 x 2^13 forward
+// 191.9 -> 183.6 us, inverse 212.9 -> 203.1 us; the same rows with the twiddle matrix lose (218.9 -> 227.1 us forward)
+// and every two-residue kernel spills, so those stay at two.
+#ifndef XNTT_MINB_ROW1
+#define XNTT_MINB_ROW1 3
+#endif
+constexpr int pass_minb(bool col, int c, bool plain) { return (!col && c == 1 && plain) ? XNTT_MINB_ROW1 : XNTT_MINB; }
 constexpr int tile_c(int logn) { return (!XNTT_FORCE_C1 && tile_logw(logn) >= 1) ? 2 : 1; }
 
 // Narrow tiles: a quarter of the residues of a whole tile, i.e. four times the CTAs and a quarter of the work per

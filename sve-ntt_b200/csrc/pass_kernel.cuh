@@ -823,7 +823,7 @@ __device__ __forceinline__ void tile_origin(const PassParams& prm, u32 tile, u64
 
 #if !defined(XNTT_HOST_EMU)
 template <class F, int LOGN, int LOGW, int C, bool COL, bool INVERSE, int TWIST, bool MAP = false>
-__global__ void __launch_bounds__(kThreads, XNTT_MINB) pass_kernel(const __grid_constant__ PassParams prm) {
+__global__ void __launch_bounds__(kThreads, pass_minb(COL, C, TWIST == kNoTwist)) pass_kernel(const __grid_constant__ PassParams prm) {
   typedef PassCfg<LOGN, LOGW, C, COL, MAP> Cfg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto* sm = reinterpret_cast<typename Slot<C>::type*>(smem_raw);
