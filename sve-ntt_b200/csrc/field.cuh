@@ -47,11 +47,6 @@ inline void unpack64(u64 v, u32& lo, u32& hi) {
   hi = (u32)(v >> 32);
 }
 inline u64 mulhi64(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) >> 64); }
-// (a - b) mod 2^64 and -borrow
-inline void sub_borrow_mask(u64 a, u64 b, u64& d, u32& m) {
-  d = a - b;
-  m = a < b ? 0xffffffffu : 0u;
-}
 // (a + b) mod 2^64 and carry + addend
 inline void add_carry_plus(u64 a, u64 b, u32 addend, u64& s, u32& k) {
   s = a + b;
@@ -72,16 +67,6 @@ __device__ __forceinline__ void unpack64(u64 v, u32& lo, u32& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
 }
 __device__ __forceinline__ u64 mulhi64(u64 a, u64 b) { return __umul64hi(a, b); }
-// (a - b) mod 2^64 and m = -borrow (IADD3, IADD3.X, IADD3.X)
-__device__ __forceinline__ void sub_borrow_mask(u64 a, u64 b, u64& d, u32& m) {
-  u32 al, ah, bl, bh, dl, dh;
-  unpack64(a, al, ah);
-  unpack64(b, bl, bh);
-  asm("sub.cc.u32 %0, %3, %5;\n\tsubc.cc.u32 %1, %4, %6;\n\tsubc.u32 %2, 0, 0;"
-      : "=r"(dl), "=r"(dh), "=r"(m)
-      : "r"(al), "r"(ah), "r"(bl), "r"(bh));
-  d = pack64(dl, dh);
-}
 // (a + b) mod 2^64 and k = addend + carry
 __device__ __forceinline__ void add_carry_plus(u64 a, u64 b, u32 addend, u64& s, u32& k) {
   u32 al, ah, bl, bh, sl, sh;
@@ -153,68 +138,17 @@ struct FieldOps : K {
     return pack64(tl, th);
   }
 
-  // Montgomery product pieces (the two-sided form; the kernels use mont_diff below, tools/lab keeps comparing against
-  // this one): returns h1 = hi64(a*w), h2 = hi64(q*P) with q = a*w' mod 2^64;
-  // a*omega == h1 - h2 (mod P), the true difference lying in (-P, P).  `a` may be lazy.
-  //
-  // On sm_100a IMAD.WIDE issues at well under half the IMAD rate (measured: 8.0 vs 18.5 Tinstr/s), so the
-  // 32x32->64 products are what the kernel is bound by.  Seven of them are needed here (four for a*w, three for
-  // q*P; the eighth is the low product a*w') instead of the eight of a pair of mul.hi.u64: the low 64 bits of
-  // a*w and q*P are equal by construction, so the carry out of the low half of q*P follows from the low half
-  // of a*w:  carry2 = [L.hi < lo32(q0*P1 + q1*P0)]  with  L.hi = bits 32..63 of a*w.
-  __device__ __forceinline__ void mont_parts(u64 a, u64 w, u64 wp, u64& h1, u64& h2) const {
-    const u64 P = this->p();
-    const u32 P_LO = (u32)P, P_HI = (u32)(P >> 32);
-    (void)P_LO;
-    (void)P_HI;
-#if defined(XNTT_HOST_EMU)
-    // the same partial-product algebra, word by word, in plain C
-    const u64 q = a * wp;
-    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), w0 = (u32)w, w1 = (u32)(w >> 32);
-    const u32 q0 = (u32)q, q1 = (u32)(q >> 32);
-    const u64 x_a = (u64)a0 * w1, x_b = (u64)a1 * w0;
-    const u64 x = x_a + x_b;                       // 65-bit cross sum: carry bit xc
-    const u32 xc = x < x_a ? 1u : 0u;
-    const u32 vh = (u32)(((u64)a0 * w0) >> 32);
-    const u32 lh = (u32)x + vh;                    // L.hi
-    const u32 carry1 = lh < vh ? 1u : 0u;
-    h1 = (u64)a1 * w1 + ((x >> 32) | ((u64)xc << 32)) + carry1;
-    const u64 y_a = (u64)q0 * P_HI, y_b = (u64)q1 * P_LO;
-    const u64 y = y_a + y_b;
-    const u32 yc = y < y_a ? 1u : 0u;
-    const u32 carry2 = lh < (u32)y ? 1u : 0u;
-    h2 = (u64)q1 * P_HI + ((y >> 32) | ((u64)yc << 32)) + carry2;
-#else
-    u32 a0, a1, w0, w1, q0, q1, h1l, h1h, h2l, h2h, vl, vh;
-    unpack64(a, a0, a1);
-    unpack64(w, w0, w1);
-    unpack64(a * wp, q0, q1);
-    // a0*w0 as a full IMAD.WIDE: costs the fma pipe what IMAD.HI does, but spares the (0 : xl) addend pair
-    // ptxas builds for the IMAD.HI form (butterfly loop: 53.2 instead of 55.2 fma-pipe cycles, measured 3 % faster)
-    unpack64((u64)a0 * w0, vl, vh);
-    (void)vl;
-    asm("{\n\t.reg .u32 xl, xh, xc, lh, yl, yh, yc, t;\n\t"
-        "mul.lo.u32 xl, %4, %7;\n\tmul.hi.u32 xh, %4, %7;\n\t"  // a0*w1
-        "mad.lo.cc.u32 xl, %5, %6, xl;\n\tmadc.hi.cc.u32 xh, %5, %6, xh;\n\taddc.u32 xc, 0, 0;\n\t"  // + a1*w0
-        "add.cc.u32 lh, xl, %12;\n\t"    // L.hi, carry1
-        "madc.lo.cc.u32 %0, %5, %7, xh;\n\tmadc.hi.u32 %1, %5, %7, xc;\n\t"  // h1 = a1*w1 + {xh, xc} + carry1
-        "mul.lo.u32 yl, %8, %11;\n\tmul.hi.u32 yh, %8, %11;\n\t"  // q0*P1
-        "mad.lo.cc.u32 yl, %9, %10, yl;\n\tmadc.hi.cc.u32 yh, %9, %10, yh;\n\taddc.u32 yc, 0, 0;\n\t"  // + q1*P0
-        // carry2 = [lh < yl] as the carry of yl + ~lh  (do NOT use sub.cc -> madc here: ptxas 12.9
-        // feeds the IADD3 carry-out, i.e. NOT borrow, straight into IMAD.WIDE.X)
-        "not.b32 t, lh;\n\tadd.cc.u32 t, yl, t;\n\t"
-        "madc.lo.cc.u32 %2, %9, %11, yh;\n\tmadc.hi.u32 %3, %9, %11, yc;\n\t"  // h2 = q1*P1 + {yh, yc} + carry2
-        "}"
-        : "=r"(h1l), "=r"(h1h), "=r"(h2l), "=r"(h2h)
-        : "r"(a0), "r"(a1), "r"(w0), "r"(w1), "r"(q0), "r"(q1), "r"(P_LO), "r"(P_HI), "r"(vh));
-    h1 = pack64(h1l, h1h);
-    h2 = pack64(h2l, h2h);
-#endif
-  }
-
   // The Montgomery product as the kernels use it: u = (h1 - h2) mod 2^64 and m = -borrow (0 or 0xffffffff), so that
-  // a*omega == u - br * 2^64 (mod P).  Same algebra as mont_parts, two instructions shorter (butterfly loop on B200:
-  // 60.7 -> 57.9 cycles per warp-butterfly, tools/lab v28):
+  // a*omega == u - br * 2^64 (mod P), with h1 = hi64(a*w), h2 = hi64(q*P), q = a*w' mod 2^64: the true difference
+  // h1 - h2 lies in (-P, P).  `a` may be lazy.
+  //
+  // On sm_100a IMAD.WIDE issues at well under half the IMAD rate (measured: 8.0 vs 18.5 Tinstr/s), so the 32x32->64
+  // products are what the kernel is bound by.  Seven of them are needed here (four for a*w, three for q*P; the eighth
+  // is the low product a*w') instead of the eight of a pair of mul.hi.u64: the low 64 bits of a*w and q*P are equal by
+  // construction, so the carry out of the low half of q*P follows from the low half of a*w:
+  //   carry2 = [L.hi < lo32(q0*P1 + q1*P0)]  with  L.hi = bits 32..63 of a*w.
+  // Two instructions shorter than completing h1 and h2 separately and subtracting them (the form until round 3, kept in
+  // tools/lab/field1.cuh; butterfly loop on B200 60.7 -> 57.9 cycles per warp-butterfly, lab v28):
   //   * q = a*w' mod 2^64 with its two narrow products chained through the addend (no separate add);
   //   * carry2 = [L.hi < yl] is the BORROW of L.hi - yl, and a borrow is what the subtraction h1 - h2 that follows takes
   //     as its borrow-in: h2' = q1*P1 + {yh, yc} without the carry, u = h1 - h2' - carry2 in the same two subc - no
@@ -253,7 +187,8 @@ struct FieldOps : K {
     unpack64(wp, wp0, wp1);
     unpack64((u64)a0 * wp0, q0, q1);
     asm("mad.lo.u32 %0, %1, %2, %0;\n\tmad.lo.u32 %0, %3, %4, %0;" : "+r"(q1) : "r"(a0), "r"(wp1), "r"(a1), "r"(wp0));
-    // a0*w0 as a full IMAD.WIDE (see mont_parts)
+    // a0*w0 as a full IMAD.WIDE: costs the fma pipe what IMAD.HI does, but spares the (0 : xl) addend pair ptxas
+    // builds for the IMAD.HI form (butterfly loop: 53.2 instead of 55.2 fma-pipe cycles, measured 3 % faster)
     unpack64((u64)a0 * w0, vl, vh);
     (void)vl;
     asm("{\n\t.reg .u32 xl, xh, xc, lh, yl, yh, yc, t, h1l, h1h, h2l, h2h;\n\t"

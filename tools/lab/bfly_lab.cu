@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "field.cuh"
+#include "field1.cuh"
 #include "field2.cuh"
 #include "field3.cuh"
 #include "field4.cuh"
@@ -112,7 +113,7 @@ __device__ __forceinline__ void bfly_deferred(u64& x0, u32& e0, u64& x1, u32& e1
   const F0 f{};
   u64 h1, h2, u, s, d;
   u32 m;
-  f.mont_parts(x1, w, wp, h1, h2);  // x1 arrives repaired (e1 == 0)
+  lab::mont_parts(f, x1, w, wp, h1, h2);  // x1 arrives repaired (e1 == 0)
   sub_borrow_mask(h1, h2, u, m);
   u32 al, ah, bl, bh, sl, sh, dl, dh, ks, kd;
   unpack64(x0, al, ah);

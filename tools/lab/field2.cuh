@@ -149,7 +149,7 @@ namespace lab {
 __device__ __forceinline__ void bf_v6(u64& x0, u64& x1, u64 w, u64 wp) {
   const xntt::F0 f{};
   u64 h1, h2;
-  f.mont_parts(x1, w, wp, h1, h2);
+  lab::mont_parts(f, x1, w, wp, h1, h2);
   const u64 u = h1 - h2;
   const u64 a = x0;
   x0 = a + u;
@@ -209,7 +209,7 @@ __device__ __forceinline__ void bf_mixed(u64& x0, u64& x1, u64 w, u64 wp) {
   const xntt::F0 f{};
   u64 h1, h2, u, s, d;
   u32 m, d0, d1;
-  f.mont_parts(x1, w, wp, h1, h2);
+  lab::mont_parts(f, x1, w, wp, h1, h2);
   xntt::sub_borrow_mask(h1, h2, u, m);
   xntt::add_carry_plus(x0, u, m, s, d0);
   xntt::sub_borrow_minus(x0, u, m, d, d1);

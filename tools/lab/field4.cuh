@@ -14,7 +14,7 @@ using xntt::u64;
 __device__ __forceinline__ void bf_v23(u64& x0, u64& x1, u64 w, u64 wp) {
   const xntt::F0 f{};
   u64 h1, h2;
-  f.mont_parts(x1, w, wp, h1, h2);
+  lab::mont_parts(f, x1, w, wp, h1, h2);
   const __int128 S = (__int128)(unsigned __int128)x0 + (__int128)(unsigned __int128)h1 - (__int128)(unsigned __int128)h2;
   const __int128 D = (__int128)(unsigned __int128)x0 - (__int128)(unsigned __int128)h1 + (__int128)(unsigned __int128)h2;
   x0 = f.fix((u64)S, (u32)(u64)(S >> 64));
@@ -26,7 +26,7 @@ __device__ __forceinline__ void bf_v23(u64& x0, u64& x1, u64 w, u64 wp) {
 __device__ __forceinline__ void bf_v24(u64& x0, u64& x1, u64 w, u64 wp) {
   const xntt::F0 f{};
   u64 h1, h2;
-  f.mont_parts(x1, w, wp, h1, h2);
+  lab::mont_parts(f, x1, w, wp, h1, h2);
   u32 al, ah, bl, bh, cl, ch, sl, sh, sk, dl, dh, dk;
   xntt::unpack64(x0, al, ah);
   xntt::unpack64(h1, bl, bh);
