@@ -579,3 +579,27 @@ def test_fixed_point_flag_is_ignored_where_illegal(emu, oracle):
         out = np.empty_like(a)
         plan.forward(out.ctypes.data, a.ctypes.data)
         assert np.array_equal(out, oracle.ntt_forward(a, N, g))
+
+
+@pytest.mark.parametrize("L,splits", [(14, None), (16, [5, 5, 6]), (13, [4, 4, 5]), (15, [9, 6])])
+def test_lazy_residues_between_passes(emu, oracle, L, splits):
+    """Column passes whose consumer begins with a Montgomery product store residues uncanonicalised (forward: every
+    twist-free / handover column pass; inverse: the inner column pass of a three-pass plan, PassParams::lazy_out).
+    Inputs built from p - 1, p - 2, 0 and 1 push intermediate sums to both ends of [0, 2^64); whatever crosses a pass
+    boundary, a complete transform returns canonical words equal to the reference's (tests/ntt-reference.hpp:43-83)."""
+    m = 1 << L
+    pats = [np.full(m, P0 - 1, dtype=np.uint64),
+            np.where(np.arange(m) % 2 == 0, np.uint64(P0 - 1), np.uint64(0)).astype(np.uint64),
+            np.where(np.arange(m) % 3 == 0, np.uint64(P0 - 2), np.uint64(1)).astype(np.uint64),
+            oracle.fill_xorshift(m, SEED + 99, P0) | np.uint64(0xFFFFFC0000000000)]
+    pats[3] = np.where(pats[3] >= np.uint64(P0), np.uint64(P0 - 1), pats[3])
+    for mx in ({}, {"compact_tables": True}):
+        plan = emu.plan(L, splits=splits, **mx)
+        for a in pats:
+            out, back = np.empty_like(a), np.empty_like(a)
+            plan.forward(out.ctypes.data, a.ctypes.data)
+            assert int(out.max()) < P0
+            assert np.array_equal(out, oracle.ntt_forward(a.copy(), P0, G0)), (L, splits, mx)
+            plan.inverse(back.ctypes.data, out.ctypes.data)
+            assert np.array_equal(back, a), (L, splits, mx)
+        plan.close()

@@ -131,6 +131,33 @@ def test_edge_inputs(cuda_lib, oracle):
         plan.close()
 
 
+@pytest.mark.parametrize("L,splits", [(14, None), (16, [5, 5, 6]), (20, None), (18, [6, 6, 6])])
+def test_lazy_residues_between_passes(cuda_lib, oracle, L, splits):
+    """Column passes whose consumer begins with a Montgomery product store residues uncanonicalised (forward: every
+    twist-free / handover column pass; inverse: the inner column pass of a three-pass plan).  Inputs built from p - 1,
+    p - 2, 0 and 1 push the intermediate sums to both ends of [0, 2^64); a complete transform still returns canonical
+    words equal to the reference's (tests/ntt-reference.hpp:43-83).  Twin of tests/test_emu_plan.py."""
+    import torch
+    m = 1 << L
+    rnd = oracle.fill_xorshift(m, SEED + 99, P0) | np.uint64(0xFFFFFC0000000000)
+    pats = [np.full(m, P0 - 1, dtype=np.uint64),
+            np.where(np.arange(m) % 2 == 0, np.uint64(P0 - 1), np.uint64(0)).astype(np.uint64),
+            np.where(np.arange(m) % 3 == 0, np.uint64(P0 - 2), np.uint64(1)).astype(np.uint64),
+            np.where(rnd >= np.uint64(P0), np.uint64(P0 - 1), rnd).astype(np.uint64)]
+    for compact in (False, True):
+        plan = cuda_lib.plan(L, splits=splits, compact_tables=compact)
+        for a in pats:
+            src = dev(a)
+            out = torch.empty_like(src)
+            plan.forward(out.data_ptr(), src.data_ptr(), stream())
+            got = host(out)
+            assert (got < np.uint64(P0)).all(), "non-canonical output word"
+            assert np.array_equal(got, oracle.ntt_forward(a.copy(), P0, G0)), (L, splits, compact)
+            plan.inverse(out.data_ptr(), out.data_ptr(), stream())
+            assert np.array_equal(host(out), a), (L, splits, compact)
+        plan.close()
+
+
 def test_padic64_elementwise(cuda_lib, oracle):
     """L0 of SURVEY.md section 4: the device modmul against 128-bit integer arithmetic on random and
     edge operands (0, 1, p-1, 2^32 boundaries, lazy values >= p)."""
